@@ -1,0 +1,171 @@
+/* mmpl_b200 — C ABI of the B200-native chunk-wise causal denoising hot path.
+ *
+ * The reference (Tele-AI/MMPL) is pure Python/PyTorch and has no FFI layer: its boundary for this
+ * path is three Python call signatures plus two dict layouts. This header is the
+ * boundary a native binding of that path would use instead; mmpl_b200/_lib.py binds it with ctypes
+ * and mmpl_b200/causal_model.py mirrors the reference classes on top of it.
+ *
+ * Conventions: every function returns 0 on success or a negative MMPL_ERR_* code, the message is
+ * available from mmpl_last_error(); no exceptions cross the ABI. All data pointers are DEVICE
+ * pointers to bf16 unless stated otherwise, arrays documented as "host" are read during the call.
+ * `stream` is a cudaStream_t passed as void* (0 = default stream). The caller owns all tensors; a
+ * context owns only its activation workspace. A context is not thread-safe; use one per GPU/process.
+ * Requires an sm_100 (B200) device: there is no fallback path, calls fail with MMPL_ERR_ARCH.
+ */
+#ifndef MMPL_B200_H_
+#define MMPL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMPL_ABI_VERSION 1
+
+enum {
+  MMPL_OK = 0,
+  MMPL_ERR_SHAPE = -1, /* unsupported or inconsistent shape / stride                */
+  MMPL_ERR_ARCH = -2,  /* current device is not sm_100                              */
+  MMPL_ERR_CUDA = -3,  /* CUDA runtime / driver call failed (see mmpl_last_error()) */
+  MMPL_ERR_ARG = -4,   /* missing or invalid argument                               */
+  MMPL_ERR_STATE = -5  /* context not ready (e.g. a weight is not bound)            */
+};
+
+/* GEMM epilogues (the element-wise op that follows each nn.Linear in the reference block). */
+enum {
+  MMPL_EPI_BIAS = 0,          /* y = bf16(acc + bias)                                               */
+  MMPL_EPI_BIAS_GELU = 1,     /* bf16(gelu_tanh(y))           wan/modules/causal_model.py:267-269    */
+  MMPL_EPI_BIAS_SILU = 2,     /* bf16(silu(y))                causal_model.py:828 (time_embedding)   */
+  MMPL_EPI_BIAS_RES = 3,      /* bf16(res + y)                causal_model.py:314 (cross-attn)       */
+  MMPL_EPI_BIAS_GATE_RES = 4  /* bf16(res + bf16(y*gate_f))   causal_model.py:310,322                */
+};
+
+int mmpl_abi_version(void);
+const char* mmpl_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-kernel entry points (unit-testable pieces of CausalWanAttentionBlock.forward,
+ * wan/modules/causal_model.py:274-326).
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]); replaces nn.Linear (+ fused follow-up op).
+ * lda/ldw/ldo/ldr are row pitches in elements. residual may alias out. gate is [frames][gate_stride]
+ * (row r uses frame r / rows_per_frame). tile_n: 0 = auto, or 64/128/256. */
+int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
+                   int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
+                   const void* gate, int64_t gate_stride, int rows_per_frame, int tile_n, void* stream);
+
+/* Non-causal softmax(Q K^T * scale) V, head_dim 128; replaces flash_attention()/attention()
+ * (wan/modules/attention.py:32-185). q: [Lq, H, 128] with row pitch ldq, out likewise with ldo.
+ * KV source 0 (k0,v0: [rows0, H, 128], pitch ldkv0) and optional source 1 are read in place through
+ * `nseg` (<= 8) row segments (host arrays): segment i = rows [seg_start[i], seg_start[i]+seg_rows[i])
+ * of source seg_src[i] (seg_src may be NULL = all source 0). */
+int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
+                    int64_t ldkv0, int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1,
+                    int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
+                    int64_t ldo, float softmax_scale, void* stream);
+
+/* bf16(bf16(bf16(LayerNorm(x)) * bf16(1 + scale_f)) + shift_f); shift/scale are [frames][mod_stride]
+ * (causal_model.py:305,318; WanLayerNorm model.py:89-99). D in {256,512,1536,5120}. */
+int mmpl_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps,
+                     const void* shift, const void* scale, int64_t mod_stride, int rows_per_frame,
+                     void* stream);
+/* bf16(LayerNorm(x) * weight + bias)  (norm3, causal_model.py:314). */
+int mmpl_ln_affine(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps,
+                   const void* weight, const void* bias, void* stream);
+/* WanRMSNorm over the full row (model.py:70-86). May run in place. */
+int mmpl_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, const void* weight,
+                 float eps, void* stream);
+
+/* RMSNorm(q), RMSNorm(k), 3-D RoPE on both, roped q -> q_out, roped k and v -> KV-cache rows
+ * (causal_model.py:111-113,193-217; causal_rope_apply :27-55; causal_fps_model.py:192-217).
+ * rope_table: device double [1024][64][2] (cos,sin). Token r of frame f (r in [0, gh*gw)) goes to row
+ * kv_row[f] + r of k_dst/v_dst and uses temporal position frame_pos[f] (host int arrays [n_frames]).
+ * q_out may alias q_in. */
+int mmpl_qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, int64_t ld_in,
+                         const void* norm_q_weight, const void* norm_k_weight, const void* rope_table,
+                         void* q_out, int64_t ldq, void* k_dst, void* v_dst, int64_t ldkv, int S, int D,
+                         int gh, int gw, int n_frames, const int* frame_pos, const int* kv_row, float eps,
+                         void* stream);
+
+/* out[f][j][:] = bf16(mod[j][:] + src[f*src_fstride + j*src_jstride + :])  (causal_model.py:300,355) */
+int mmpl_modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_t src_jstride,
+                        void* out, int F, int J, int D, void* stream);
+/* sinusoidal_embedding_1d (model.py:15-25), float64 -> bf16. t: device double [F]. out: [F, dim]. */
+int mmpl_sinusoid_embedding(const double* t, void* out, int F, int dim, void* stream);
+/* Linear for M <= 32 rows with optional SiLU on the input and/or output (time MLP, causal_model.py:828-831). */
+int mmpl_skinny_linear(const void* x, int64_t ldx, const void* w, const void* b, void* out, int64_t ldo,
+                       int M, int N, int K, int silu_in, int silu_out, void* stream);
+/* im2col of the (1,2,2) patch embedding (causal_model.py:812): x is [F][C][H][W] with the given
+ * frame/channel strides; a is [F*(H/2)*(W/2), C*4]. */
+int mmpl_patchify(const void* x, int64_t stride_f, int64_t stride_c, void* a, int F, int C, int H, int W,
+                  void* stream);
+/* unpatchify (causal_model.py:1094-1117) -> flow [F][C][H][W]; if x0 != NULL also
+ * x0 = bf16(double(xt) - sigma_f * double(flow)) (utils/wan_wrapper.py:172-196). sigma: device double [F]. */
+int mmpl_unpatchify_x0(const void* head, int64_t ldh, const void* xt, int64_t xt_stride_f,
+                       int64_t xt_stride_c, const double* sigma, void* flow, void* x0, int F, int C, int H,
+                       int W, void* stream);
+/* FlowMatchScheduler.add_noise (utils/scheduler.py:159-176): bf16((1-sigma_f)*x0 + sigma_f*noise), fp32.
+ * sigma: device float [n_frames]; tensors are [n_frames][per_frame] contiguous. */
+int mmpl_add_noise(const void* x0, const void* noise, const float* sigma, void* out, int n_frames,
+                   int64_t per_frame, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-forward entry point: CausalWanModel._forward_inference (causal_model.py:763-892) and the
+ * KV-cache branch of CausalFPSWanModel (causal_fps_model.py:192-264) for batch size 1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mmpl_ctx mmpl_ctx;
+
+typedef struct {
+  int dim, ffn_dim, num_heads, num_layers;
+  int freq_dim, text_dim, text_len, in_dim, out_dim;
+  float eps;
+  int max_tokens; /* workspace capacity: largest n_frames * tokens-per-frame of any forward */
+} mmpl_model_config;
+
+int mmpl_ctx_create(const mmpl_model_config* cfg, mmpl_ctx** out);
+void mmpl_ctx_destroy(mmpl_ctx* ctx);
+/* Bind a parameter by its reference state-dict name (causal_model.py module tree), e.g.
+ * "blocks.3.self_attn.o.weight", "head.modulation", "patch_embedding.weight"; the fused
+ * [3*dim, dim] q/k/v projection is bound as "blocks.N.self_attn.qkv.{weight,bias}". The pointer must
+ * stay valid while the context is used. */
+int mmpl_bind_weight(mmpl_ctx* ctx, const char* name, const void* ptr, int64_t numel);
+int mmpl_bind_rope_table(mmpl_ctx* ctx, const void* table /* device double [1024][64][2] */);
+/* Number of kernels the context launched since the last call with reset != 0. */
+int64_t mmpl_launch_count(mmpl_ctx* ctx, int reset);
+
+typedef struct {
+  /* latent chunk [n_frames][in_dim][lat_h][lat_w] (strides in elements) */
+  const void* latents;
+  int64_t lat_stride_f, lat_stride_c;
+  int n_frames, lat_h, lat_w;
+  const double* timesteps; /* device [n_frames] */
+  const void* context;     /* [text_len, text_dim]; required when cross_init == 0 */
+  /* self-attention KV cache: host arrays [num_layers] of device pointers to [cache_rows, H, 128] */
+  void* const* kv_k;
+  void* const* kv_v;
+  int64_t cache_rows;
+  const int* frame_pos; /* host [n_frames]: temporal RoPE position of each frame                  */
+  const int* kv_row;    /* host [n_frames]: cache row receiving each frame's first token           */
+  int kv_to_tail;       /* 1: K/V of this call are NOT written to the cache but attended as an extra
+                           trailing segment (last MMPL stage, causal_fps_model.py:254-264)          */
+  int n_seg;            /* cache row segments attended after the write (host arrays, <= 7)         */
+  const int* seg_start;
+  const int* seg_rows;
+  /* cross-attention cache: host arrays [num_layers] of device pointers to [text_len, H, 128] */
+  void* const* cross_k;
+  void* const* cross_v;
+  int cross_init; /* 0: compute K/V from `context` into cross_k/cross_v first (model.py:174-180)  */
+  /* outputs, [n_frames][out_dim][lat_h][lat_w] contiguous */
+  void* flow;
+  void* x0;            /* may be NULL */
+  const double* sigma; /* device [n_frames], required when x0 != NULL */
+} mmpl_forward_args;
+
+int mmpl_forward(mmpl_ctx* ctx, const mmpl_forward_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMPL_B200_H_ */

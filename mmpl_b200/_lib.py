@@ -1,0 +1,113 @@
+"""ctypes binding of the C ABI declared in include/mmpl_b200.h.
+
+`load()` returns the library with argtypes set for every exported symbol; `check(status)` turns a
+negative status into a Python exception carrying mmpl_last_error(). Nothing here computes anything:
+if the shared library is missing (and cannot be built) loading raises, there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import _build
+
+_LIB = None
+
+c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
+c_int_p = C.POINTER(C.c_int)
+c_void_pp = C.POINTER(C.c_void_p)
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("dim", c_int), ("ffn_dim", c_int), ("num_heads", c_int), ("num_layers", c_int),
+        ("freq_dim", c_int), ("text_dim", c_int), ("text_len", c_int), ("in_dim", c_int), ("out_dim", c_int),
+        ("eps", c_float), ("max_tokens", c_int),
+    ]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("latents", c_void_p), ("lat_stride_f", c_int64), ("lat_stride_c", c_int64),
+        ("n_frames", c_int), ("lat_h", c_int), ("lat_w", c_int),
+        ("timesteps", c_void_p), ("context", c_void_p),
+        ("kv_k", c_void_pp), ("kv_v", c_void_pp), ("cache_rows", c_int64),
+        ("frame_pos", c_int_p), ("kv_row", c_int_p), ("kv_to_tail", c_int),
+        ("n_seg", c_int), ("seg_start", c_int_p), ("seg_rows", c_int_p),
+        ("cross_k", c_void_pp), ("cross_v", c_void_pp), ("cross_init", c_int),
+        ("flow", c_void_p), ("x0", c_void_p), ("sigma", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every function declared in include/mmpl_b200.h
+SIGNATURES = {
+    "mmpl_abi_version": (c_int, []),
+    "mmpl_last_error": (C.c_char_p, []),
+    "mmpl_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                               c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "mmpl_flash_attn": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                c_int64, c_int, c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_int64, c_float, c_void_p]),
+    "mmpl_ln_modulate": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p,
+                                 c_int64, c_int, c_void_p]),
+    "mmpl_ln_affine": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "mmpl_rmsnorm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
+    "mmpl_qk_norm_rope_kv": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int_p,
+                                     c_int_p, c_float, c_void_p]),
+    "mmpl_modulation_add": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mmpl_sinusoid_embedding": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmpl_skinny_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p]),
+    "mmpl_patchify": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmpl_unpatchify_x0": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_int, c_int, c_int, c_void_p]),
+    "mmpl_add_noise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "mmpl_ctx_create": (c_int, [C.POINTER(ModelConfig), C.POINTER(c_void_p)]),
+    "mmpl_ctx_destroy": (None, [c_void_p]),
+    "mmpl_bind_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int64]),
+    "mmpl_bind_rope_table": (c_int, [c_void_p, c_void_p]),
+    "mmpl_launch_count": (c_int64, [c_void_p, c_int]),
+    "mmpl_forward": (c_int, [c_void_p, C.POINTER(ForwardArgs), c_void_p]),
+}
+
+
+class MmplError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"mmpl_b200 error {status}: {message}")
+        self.status = status
+
+
+def lib_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load libmmpl_b200.so (building it with nvcc if it is missing or older than its sources)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build_library()
+        except Exception:
+            if not path.exists():
+                raise
+    if not path.exists():
+        raise ImportError(f"{path} is missing: build it with `python -m mmpl_b200._build` (needs nvcc); "
+                          "mmpl_b200 has no CPU fallback")
+    lib = C.CDLL(str(path))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.mmpl_abi_version() != 1:
+        raise ImportError("libmmpl_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().mmpl_last_error()
+        raise MmplError(status, msg.decode() if msg else "")

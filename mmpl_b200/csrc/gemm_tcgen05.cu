@@ -1,0 +1,312 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:
+//   out[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )      (bf16 in, fp32 accumulate in TMEM)
+// This is every nn.Linear on the CausalWanModel hot path (reference: wan/modules/causal_model.py:
+// 111-113 q/k/v, :230 o, :267-269 ffn; wan/modules/model.py:172-193 cross-attention), with the
+// element-wise work that follows each Linear in the reference folded into the epilogue at the
+// reference's own bf16 rounding points:
+//   EPI_BIAS           y = bf16(acc + b)
+//   EPI_BIAS_GELU      bf16(gelu_tanh(y))                         (ffn.1, causal_model.py:268)
+//   EPI_BIAS_SILU      bf16(silu(y))                              (time_embedding.1)
+//   EPI_BIAS_RES       bf16(res + y)                              (cross-attn residual, :314)
+//   EPI_BIAS_GATE_RES  bf16(res + bf16(y * gate[frame(row)]))     (:310, :322)
+//
+// Structure: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue.
+// A/W tiles are [128|BN rows] x [64 k] bf16 boxes in 128B-swizzled smem; the 128 x BN fp32
+// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "host_util.h"
+#include "mmpl_b200.h"
+#include "ptx.cuh"
+
+namespace mmpl {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+
+struct GemmParams {
+  int M, N, K;
+  __nv_bfloat16* out;
+  int64_t ldo;
+  const __nv_bfloat16* bias;  // may be null
+  const __nv_bfloat16* res;   // residual, may alias out
+  int64_t ldr;
+  const __nv_bfloat16* gate;  // [frames][gate_stride] vectors of N
+  int64_t gate_stride;
+  int rows_per_frame;
+  int tiles_m, tiles_n;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
+  const float kKappa = 0.044715f;
+  float inner = kBeta * (x + kKappa * x * x * x);
+  // tanh(u) = 1 - 2 / (exp(2u) + 1)
+  float t = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int ST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + ST * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + ST;
+  uint64_t* tmem_full = bars + 2 * ST;
+  uint64_t* tmem_empty = bars + 2 * ST + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < ST; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % p.tiles_m;
+        const int n_blk = t / p.tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(smem_a + s * Cfg::kABytes, &map_a, &full_bar[s], kb * kBK, m_blk * kBM, kEvictNormal);
+          tma_load_2d(smem_b + s * Cfg::kBBytes, &map_b, &full_bar[s], kb * kBK, n_blk * BN, kEvictLast);
+          if (++s == ST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::kABytes), 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes (= 2 in the >>4 address field) per 16-element K step inside the swizzle atom
+            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);
+          if (kb == num_kb - 1) tc_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m_blk = t % p.tiles_m;
+      const int n_blk = t / p.tiles_m;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      const int row = m_blk * kBM + lane_base + lane;
+      const bool row_ok = row < p.M;
+      const __nv_bfloat16* gate_row = nullptr;
+      if (EPI == MMPL_EPI_BIAS_GATE_RES && row_ok)
+        gate_row = p.gate + static_cast<int64_t>(row / p.rows_per_frame) * p.gate_stride;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN + c * 32, acc);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+          // N is a multiple of 8; handle the chunk in 8-column (16-byte) groups.
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= p.N) break;
+            uint4 bv = make_uint4(0, 0, 0, 0);
+            if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+            uint4 rv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
+            if (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES)
+              rv = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(row) * p.ldr + col);
+            if (EPI == MMPL_EPI_BIAS_GATE_RES)
+              gv = __ldg(reinterpret_cast<const uint4*>(gate_row + col));
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+              float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+              if (EPI == MMPL_EPI_BIAS_GELU) {
+                y0 = gelu_tanh_f(y0);
+                y1 = gelu_tanh_f(y1);
+              } else if (EPI == MMPL_EPI_BIAS_SILU) {
+                y0 = silu_f(y0);
+                y1 = silu_f(y1);
+              } else if (EPI == MMPL_EPI_BIAS_RES) {
+                y0 = bf16_lo(rw[j]) + y0;
+                y1 = bf16_hi(rw[j]) + y1;
+              } else if (EPI == MMPL_EPI_BIAS_GATE_RES) {
+                y0 = bf16_lo(rw[j]) + bf16_round(y0 * bf16_lo(gw[j]));
+                y1 = bf16_hi(rw[j]) + bf16_round(y1 * bf16_hi(gw[j]));
+              }
+              ow[j] = pack_bf16x2(y0, y1);
+            }
+            *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row) * p.ldo + col) =
+                make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + kBM - 1) / kBM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*ma, *mb, p);
+  MMPL_CUDA(cudaGetLastError());
+  return MMPL_OK;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap* ma, const CUtensorMap* mb, const GemmParams& p,
+                        cudaStream_t stream) {
+  switch (epi) {
+    case MMPL_EPI_BIAS: return launch_gemm<BN, MMPL_EPI_BIAS>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GELU: return launch_gemm<BN, MMPL_EPI_BIAS_GELU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_SILU: return launch_gemm<BN, MMPL_EPI_BIAS_SILU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_RES: return launch_gemm<BN, MMPL_EPI_BIAS_RES>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GATE_RES: return launch_gemm<BN, MMPL_EPI_BIAS_GATE_RES>(ma, mb, p, stream);
+    default: set_error("gemm: unknown epilogue %d", epi); return MMPL_ERR_ARG;
+  }
+}
+
+// Tile width: 256 when it keeps the machine full, otherwise narrower tiles for more CTAs.
+static int pick_bn(int M, int N) {
+  if (N % 128 != 0 || N < 128) return 64;
+  const int tiles_m = (M + kBM - 1) / kBM;
+  if (N % 256 == 0) {
+    const int t256 = tiles_m * (N / 256);
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    // wave efficiency of each choice: tiles / (ceil(tiles / sms) * sms)
+    const int t128 = tiles_m * (N / 128);
+    const double e256 = double(t256) / (double((t256 + sms - 1) / sms) * sms);
+    const double e128 = double(t128) / (double((t128 + sms - 1) / sms) * sms);
+    return (e256 + 0.08 >= e128) ? 256 : 128;
+  }
+  return 128;
+}
+
+int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
+              int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
+              const void* gate, int64_t gate_stride, int rows_per_frame, int force_bn,
+              cudaStream_t stream) {
+  MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "gemm: requires an sm_100 device");
+  MMPL_CHECK(M > 0 && N > 0 && K > 0, MMPL_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  MMPL_CHECK(N % 8 == 0 && K % 8 == 0 && ldo % 8 == 0, MMPL_ERR_SHAPE,
+             "gemm: N, K and ldo must be multiples of 8 (N=%d K=%d ldo=%lld)", N, K, (long long)ldo);
+  if (epilogue == MMPL_EPI_BIAS_RES || epilogue == MMPL_EPI_BIAS_GATE_RES)
+    MMPL_CHECK(residual != nullptr && ldr % 8 == 0, MMPL_ERR_ARG, "gemm: residual epilogue needs residual with ldr %% 8 == 0");
+  if (epilogue == MMPL_EPI_BIAS_GATE_RES)
+    MMPL_CHECK(gate != nullptr && rows_per_frame > 0 && gate_stride % 8 == 0, MMPL_ERR_ARG,
+               "gemm: gate epilogue needs gate, rows_per_frame > 0 and gate_stride %% 8 == 0");
+  const int bn = force_bn ? force_bn : pick_bn(M, N);
+  MMPL_CHECK(bn == 64 || bn == 128 || bn == 256, MMPL_ERR_ARG, "gemm: tile width %d not supported", bn);
+
+  const CUtensorMap* ma = get_tensor_map_bf16(a, M, K, lda, kBM);
+  const CUtensorMap* mb = get_tensor_map_bf16(w, N, K, ldw, bn);
+  if (!ma || !mb) return MMPL_ERR_CUDA;
+
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.res = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = ldr;
+  p.gate = static_cast<const __nv_bfloat16*>(gate);
+  p.gate_stride = gate_stride;
+  p.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
+  if (bn == 256) return dispatch_epi<256>(epilogue, ma, mb, p, stream);
+  if (bn == 128) return dispatch_epi<128>(epilogue, ma, mb, p, stream);
+  return dispatch_epi<64>(epilogue, ma, mb, p, stream);
+}
+
+}  // namespace mmpl

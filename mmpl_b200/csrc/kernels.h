@@ -1,0 +1,38 @@
+// Internal C++ launchers behind the C ABI (include/mmpl_b200.h). Each returns an MMPL_* status.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mmpl {
+
+int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
+              int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
+              const void* gate, int64_t gate_stride, int rows_per_frame, int force_bn, cudaStream_t stream);
+
+int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
+                    int64_t ldkv0, int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1,
+                    int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
+                    int64_t ldo, float softmax_scale, cudaStream_t stream);
+
+int ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
+                const void* scale, int64_t mod_stride, int rows_per_frame, cudaStream_t st);
+int ln_affine(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* weight,
+              const void* bias, cudaStream_t st);
+int rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, const void* weight, float eps,
+            cudaStream_t st);
+int qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, int64_t ld_in, const void* wq,
+                    const void* wk, const void* rope_table, void* q_out, int64_t ldq, void* k_dst, void* v_dst,
+                    int64_t ldkv, int S, int D, int gh, int gw, int n_frames, const int* frame_pos,
+                    const int* kv_row, float eps, cudaStream_t st);
+int modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_t src_jstride, void* out, int F,
+                   int J, int D, cudaStream_t st);
+int sinusoid_embedding(const double* t, void* out, int F, int dim, cudaStream_t st);
+int skinny_linear(const void* x, int64_t ldx, const void* w, const void* b, void* out, int64_t ldo, int M, int N,
+                  int K, int silu_in, int silu_out, cudaStream_t st);
+int patchify(const void* x, int64_t stride_f, int64_t stride_c, void* a, int F, int C, int H, int W, cudaStream_t st);
+int unpatchify_x0(const void* head, int64_t ldh, const void* xt, int64_t xt_stride_f, int64_t xt_stride_c,
+                  const double* sigma, void* flow, void* x0, int F, int C, int H, int W, cudaStream_t st);
+int add_noise(const void* x0, const void* noise, const float* sigma, void* out, int n_frames, int64_t per_frame,
+              cudaStream_t st);
+
+}  // namespace mmpl
