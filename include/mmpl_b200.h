@@ -134,6 +134,16 @@ int mmpl_bind_weight(mmpl_ctx* ctx, const char* name, const void* ptr, int64_t n
 int mmpl_bind_rope_table(mmpl_ctx* ctx, const void* table /* device double [1024][64][2] */);
 /* Number of kernels the context launched since the last call with reset != 0. */
 int64_t mmpl_launch_count(mmpl_ctx* ctx, int reset);
+/* Kernels launched through any entry point of this library in this process (bench.py "gpu_launches"). */
+int64_t mmpl_total_launches(int reset);
+
+/* Device timing by kernel category for the roofline report: when a category's bit is set in `category_mask`,
+ * mmpl_forward brackets each launch of that category with CUDA events on the launch stream.
+ * mmpl_profile_read synchronises those events and returns, per category, the summed milliseconds, the summed
+ * algorithmic work (FLOPs for categories 0-2, bytes for 3) and the launch count. */
+enum { MMPL_PROF_SELF_ATTN = 0, MMPL_PROF_CROSS_ATTN = 1, MMPL_PROF_GEMM = 2, MMPL_PROF_POINTWISE = 3, MMPL_PROF_NCAT = 4 };
+int mmpl_profile_enable(mmpl_ctx* ctx, int category_mask);
+int mmpl_profile_read(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches, int reset);
 
 typedef struct {
   /* latent chunk [n_frames][in_dim][lat_h][lat_w] (strides in elements) */

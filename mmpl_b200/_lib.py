@@ -68,6 +68,9 @@ SIGNATURES = {
     "mmpl_bind_rope_table": (c_int, [c_void_p, c_void_p]),
     "mmpl_launch_count": (c_int64, [c_void_p, c_int]),
     "mmpl_forward": (c_int, [c_void_p, C.POINTER(ForwardArgs), c_void_p]),
+    "mmpl_total_launches": (c_int64, [c_int]),
+    "mmpl_profile_enable": (c_int, [c_void_p, c_int]),
+    "mmpl_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),
 }
 
 

@@ -76,6 +76,14 @@ struct mmpl_ctx {
   GlobalWeights g;
   const void* rope_table = nullptr;
   int64_t launches = 0;
+  // optional per-category device timing (bench.py roofline): events around every launch of a category
+  int profile_mask = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<int, std::pair<size_t, size_t>>> ev_spans;  // (category, (start idx, stop idx))
+  double prof_ms[MMPL_PROF_NCAT] = {0, 0, 0, 0};
+  int64_t prof_launches[MMPL_PROF_NCAT] = {0, 0, 0, 0};
+  double prof_work[MMPL_PROF_NCAT] = {0, 0, 0, 0};  // algorithmic FLOPs (cat 0-2) or bytes (cat 3)
   // workspace (device)
   char* ws = nullptr;
   size_t ws_bytes = 0;
@@ -83,6 +91,14 @@ struct mmpl_ctx {
   void *sinus = nullptr, *t1 = nullptr, *e = nullptr, *e0 = nullptr, *emod = nullptr, *ehead = nullptr;
   void *ctx_h = nullptr, *ctx_e = nullptr, *tail_k = nullptr, *tail_v = nullptr;
 };
+
+static int64_t g_total_launches = 0;
+#define COUNTED(call)                         \
+  do {                                        \
+    const int _s = (call);                    \
+    if (_s == MMPL_OK) ++g_total_launches;    \
+    return _s;                                \
+  } while (0)
 
 extern "C" {
 
@@ -92,8 +108,8 @@ const char* mmpl_last_error(void) { return last_error_buf(); }
 int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
                    int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
                    const void* gate, int64_t gate_stride, int rows_per_frame, int tile_n, void* stream) {
-  return gemm_bf16(a, lda, w, ldw, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate, gate_stride,
-                   rows_per_frame, tile_n, static_cast<cudaStream_t>(stream));
+  COUNTED(gemm_bf16(a, lda, w, ldw, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate, gate_stride,
+                   rows_per_frame, tile_n, static_cast<cudaStream_t>(stream)));
 }
 
 int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0, int64_t ldkv0,
@@ -101,22 +117,22 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                     const int* seg_start, const int* seg_rows, const int* seg_src, void* out, int64_t ldo,
                     float softmax_scale, void* stream) {
   MMPL_CHECK(q && k0 && v0 && out && seg_start && seg_rows, MMPL_ERR_ARG, "flash_attn: null argument");
-  return flash_attn_bf16(q, ldq, Lq, H, k0, v0, ldkv0, rows0, k1, v1, ldkv1, rows1, nseg, seg_start, seg_rows,
-                         seg_src, out, ldo, softmax_scale, static_cast<cudaStream_t>(stream));
+  COUNTED(flash_attn_bf16(q, ldq, Lq, H, k0, v0, ldkv0, rows0, k1, v1, ldkv1, rows1, nseg, seg_start, seg_rows,
+                         seg_src, out, ldo, softmax_scale, static_cast<cudaStream_t>(stream)));
 }
 
 int mmpl_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                      const void* scale, int64_t mod_stride, int rows_per_frame, void* stream) {
-  return ln_modulate(x, ldx, out, ldo, S, D, eps, shift, scale, mod_stride, rows_per_frame,
-                     static_cast<cudaStream_t>(stream));
+  COUNTED(ln_modulate(x, ldx, out, ldo, S, D, eps, shift, scale, mod_stride, rows_per_frame,
+                     static_cast<cudaStream_t>(stream)));
 }
 int mmpl_ln_affine(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* weight,
                    const void* bias, void* stream) {
-  return ln_affine(x, ldx, out, ldo, S, D, eps, weight, bias, static_cast<cudaStream_t>(stream));
+  COUNTED(ln_affine(x, ldx, out, ldo, S, D, eps, weight, bias, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, const void* weight, float eps,
                  void* stream) {
-  return rmsnorm(x, ldx, out, ldo, S, D, weight, eps, static_cast<cudaStream_t>(stream));
+  COUNTED(rmsnorm(x, ldx, out, ldo, S, D, weight, eps, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, int64_t ld_in,
                          const void* norm_q_weight, const void* norm_k_weight, const void* rope_table, void* q_out,
@@ -125,32 +141,32 @@ int mmpl_qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, i
   MMPL_CHECK(q_in && k_in && v_in && norm_q_weight && norm_k_weight && rope_table && q_out && k_dst && v_dst &&
                  frame_pos && kv_row,
              MMPL_ERR_ARG, "qk_norm_rope_kv: null argument");
-  return qk_norm_rope_kv(q_in, k_in, v_in, ld_in, norm_q_weight, norm_k_weight, rope_table, q_out, ldq, k_dst, v_dst,
-                         ldkv, S, D, gh, gw, n_frames, frame_pos, kv_row, eps, static_cast<cudaStream_t>(stream));
+  COUNTED(qk_norm_rope_kv(q_in, k_in, v_in, ld_in, norm_q_weight, norm_k_weight, rope_table, q_out, ldq, k_dst, v_dst,
+                         ldkv, S, D, gh, gw, n_frames, frame_pos, kv_row, eps, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_t src_jstride, void* out, int F,
                         int J, int D, void* stream) {
-  return modulation_add(mod, src, src_fstride, src_jstride, out, F, J, D, static_cast<cudaStream_t>(stream));
+  COUNTED(modulation_add(mod, src, src_fstride, src_jstride, out, F, J, D, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_sinusoid_embedding(const double* t, void* out, int F, int dim, void* stream) {
-  return sinusoid_embedding(t, out, F, dim, static_cast<cudaStream_t>(stream));
+  COUNTED(sinusoid_embedding(t, out, F, dim, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_skinny_linear(const void* x, int64_t ldx, const void* w, const void* b, void* out, int64_t ldo, int M, int N,
                        int K, int silu_in, int silu_out, void* stream) {
-  return skinny_linear(x, ldx, w, b, out, ldo, M, N, K, silu_in, silu_out, static_cast<cudaStream_t>(stream));
+  COUNTED(skinny_linear(x, ldx, w, b, out, ldo, M, N, K, silu_in, silu_out, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_patchify(const void* x, int64_t stride_f, int64_t stride_c, void* a, int F, int C, int H, int W,
                   void* stream) {
-  return patchify(x, stride_f, stride_c, a, F, C, H, W, static_cast<cudaStream_t>(stream));
+  COUNTED(patchify(x, stride_f, stride_c, a, F, C, H, W, static_cast<cudaStream_t>(stream)));
 }
 int mmpl_unpatchify_x0(const void* head, int64_t ldh, const void* xt, int64_t xt_stride_f, int64_t xt_stride_c,
                        const double* sigma, void* flow, void* x0, int F, int C, int H, int W, void* stream) {
-  return unpatchify_x0(head, ldh, xt, xt_stride_f, xt_stride_c, sigma, flow, x0, F, C, H, W,
-                       static_cast<cudaStream_t>(stream));
+  COUNTED(unpatchify_x0(head, ldh, xt, xt_stride_f, xt_stride_c, sigma, flow, x0, F, C, H, W,
+                       static_cast<cudaStream_t>(stream)));
 }
 int mmpl_add_noise(const void* x0, const void* noise, const float* sigma, void* out, int n_frames, int64_t per_frame,
                    void* stream) {
-  return add_noise(x0, noise, sigma, out, n_frames, per_frame, static_cast<cudaStream_t>(stream));
+  COUNTED(add_noise(x0, noise, sigma, out, n_frames, per_frame, static_cast<cudaStream_t>(stream)));
 }
 
 // ------------------------------------------------------------------------------------------------ context
@@ -252,12 +268,65 @@ int64_t mmpl_launch_count(mmpl_ctx* ctx, int reset) {
   return n;
 }
 
-#define RUN(call)                  \
-  do {                             \
-    const int _s = (call);         \
-    if (_s != MMPL_OK) return _s;  \
-    ++ctx->launches;               \
+static cudaEvent_t prof_event(mmpl_ctx* ctx) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev_pool.push_back(e);
+  }
+  return ctx->ev_pool[ctx->ev_used++];
+}
+
+// RUN(category, algorithmic work, launcher call)
+#define RUN(cat, work, call)                                                  \
+  do {                                                                        \
+    const bool _prof = (ctx->profile_mask >> (cat)) & 1;                      \
+    size_t _i0 = 0;                                                           \
+    if (_prof) { _i0 = ctx->ev_used; cudaEventRecord(prof_event(ctx), st); }  \
+    const int _s = (call);                                                    \
+    if (_s != MMPL_OK) return _s;                                             \
+    if (_prof) {                                                              \
+      const size_t _i1 = ctx->ev_used;                                        \
+      cudaEventRecord(prof_event(ctx), st);                                   \
+      ctx->ev_spans.push_back({(cat), {_i0, _i1}});                           \
+      ctx->prof_work[(cat)] += (work);                                        \
+      ++ctx->prof_launches[(cat)];                                            \
+    }                                                                         \
+    ++ctx->launches;                                                          \
+    ++g_total_launches;                                                       \
   } while (0)
+
+int mmpl_profile_enable(mmpl_ctx* ctx, int category_mask) {
+  MMPL_CHECK(ctx, MMPL_ERR_ARG, "profile_enable: null context");
+  ctx->profile_mask = category_mask;
+  return MMPL_OK;
+}
+
+int mmpl_profile_read(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches, int reset) {
+  MMPL_CHECK(ctx && ms && work && launches, MMPL_ERR_ARG, "profile_read: null argument");
+  for (auto& sp : ctx->ev_spans) {
+    cudaEvent_t a = ctx->ev_pool[sp.second.first], b = ctx->ev_pool[sp.second.second];
+    MMPL_CUDA(cudaEventSynchronize(b));
+    float t = 0.f;
+    MMPL_CUDA(cudaEventElapsedTime(&t, a, b));
+    ctx->prof_ms[sp.first] += t;
+  }
+  ctx->ev_spans.clear();
+  ctx->ev_used = 0;
+  for (int i = 0; i < MMPL_PROF_NCAT; ++i) {
+    ms[i] = ctx->prof_ms[i];
+    work[i] = ctx->prof_work[i];
+    launches[i] = ctx->prof_launches[i];
+    if (reset) { ctx->prof_ms[i] = 0; ctx->prof_work[i] = 0; ctx->prof_launches[i] = 0; }
+  }
+  return MMPL_OK;
+}
+
+int64_t mmpl_total_launches(int reset) {
+  const int64_t n = g_total_launches;
+  if (reset) g_total_launches = 0;
+  return n;
+}
 
 int mmpl_forward(mmpl_ctx* ctx, const mmpl_forward_args* a, void* stream_v) {
   MMPL_CHECK(ctx && a, MMPL_ERR_ARG, "forward: null argument");
@@ -300,18 +369,18 @@ int mmpl_forward(mmpl_ctx* ctx, const mmpl_forward_args* a, void* stream_v) {
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)
 
   // patch embedding (causal_model.py:812-818)
-  RUN(patchify(a->latents, a->lat_stride_f, a->lat_stride_c, ctx->patch, F, c.in_dim, a->lat_h, a->lat_w, st));
-  RUN(gemm_bf16(ctx->patch, PK, g.patch_w, PK, g.patch_b, x, D, S, D, PK, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+  RUN(3, 4.0 * S * PK, patchify(a->latents, a->lat_stride_f, a->lat_stride_c, ctx->patch, F, c.in_dim, a->lat_h, a->lat_w, st));
+  RUN(2, 2.0 * S * D * PK, gemm_bf16(ctx->patch, PK, g.patch_w, PK, g.patch_b, x, D, S, D, PK, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
   // time embedding and projection (causal_model.py:828-831)
-  RUN(sinusoid_embedding(a->timesteps, ctx->sinus, F, c.freq_dim, st));
-  RUN(skinny_linear(ctx->sinus, c.freq_dim, g.time0_w, g.time0_b, ctx->t1, D, F, D, c.freq_dim, 0, 1, st));
-  RUN(skinny_linear(ctx->t1, D, g.time2_w, g.time2_b, ctx->e, D, F, D, D, 0, 0, st));
-  RUN(skinny_linear(ctx->e, D, g.tproj_w, g.tproj_b, e0, 6 * D, F, 6 * D, D, 1, 0, st));
+  RUN(3, 0.0, sinusoid_embedding(a->timesteps, ctx->sinus, F, c.freq_dim, st));
+  RUN(3, 2.0 * D * c.freq_dim, skinny_linear(ctx->sinus, c.freq_dim, g.time0_w, g.time0_b, ctx->t1, D, F, D, c.freq_dim, 0, 1, st));
+  RUN(3, 2.0 * D * D, skinny_linear(ctx->t1, D, g.time2_w, g.time2_b, ctx->e, D, F, D, D, 0, 0, st));
+  RUN(3, 12.0 * D * D, skinny_linear(ctx->e, D, g.tproj_w, g.tproj_b, e0, 6 * D, F, 6 * D, D, 1, 0, st));
   // text embedding, only when the cross-attention K/V must be (re)computed (causal_model.py:836-841)
   if (!a->cross_init) {
-    RUN(gemm_bf16(a->context, c.text_dim, g.text0_w, c.text_dim, g.text0_b, ctx->ctx_h, D, T, D, c.text_dim,
+    RUN(2, 2.0 * T * D * c.text_dim, gemm_bf16(a->context, c.text_dim, g.text0_w, c.text_dim, g.text0_b, ctx->ctx_h, D, T, D, c.text_dim,
                   MMPL_EPI_BIAS_GELU, nullptr, 0, nullptr, 0, 0, 0, st));
-    RUN(gemm_bf16(ctx->ctx_h, D, g.text2_w, D, g.text2_b, ctx->ctx_e, D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+    RUN(2, 2.0 * T * D * D, gemm_bf16(ctx->ctx_h, D, g.text2_w, D, g.text2_b, ctx->ctx_e, D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
   }
 
   int seg_start[8], seg_rows[8], seg_src[8];
@@ -328,45 +397,47 @@ int mmpl_forward(mmpl_ctx* ctx, const mmpl_forward_args* a, void* stream_v) {
     ++nseg;
   }
   const int cross_start = 0, cross_rows = T;
+  double lk_self = 0;
+  for (int i = 0; i < nseg; ++i) lk_self += seg_rows[i];
 
   for (int l = 0; l < L; ++l) {
     const LayerWeights& w = ctx->layers[l];
     bf* kc = static_cast<bf*>(a->kv_k[l]);
     bf* vc = static_cast<bf*>(a->kv_v[l]);
     // e = modulation + e0 (causal_model.py:300)
-    RUN(modulation_add(w.modulation, e0, 6 * D, D, emod, F, 6, D, st));
+    RUN(3, 0.0, modulation_add(w.modulation, e0, 6 * D, D, emod, F, 6, D, st));
     // self-attention (causal_model.py:304-310, 86-231)
-    RUN(ln_modulate(x, D, xm, D, S, D, c.eps, emod + 0 * D, emod + 1 * D, 6 * D, fs, st));
-    RUN(gemm_bf16(xm, D, w.qkv_w, D, w.qkv_b, qkv, 3 * D, S, 3 * D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
-    RUN(qk_norm_rope_kv(qkv, qkv + D, qkv + 2 * D, 3 * D, w.norm_q, w.norm_k, ctx->rope_table, qkv, 3 * D,
+    RUN(3, 4.0 * S * D, ln_modulate(x, D, xm, D, S, D, c.eps, emod + 0 * D, emod + 1 * D, 6 * D, fs, st));
+    RUN(2, 6.0 * S * D * D, gemm_bf16(xm, D, w.qkv_w, D, w.qkv_b, qkv, 3 * D, S, 3 * D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+    RUN(3, 12.0 * S * D, qk_norm_rope_kv(qkv, qkv + D, qkv + 2 * D, 3 * D, w.norm_q, w.norm_k, ctx->rope_table, qkv, 3 * D,
                         a->kv_to_tail ? ctx->tail_k : kc, a->kv_to_tail ? ctx->tail_v : vc, D, S, D, gh, gw, F,
                         a->frame_pos, a->kv_row, c.eps, st));
-    RUN(flash_attn_bf16(qkv, 3 * D, S, H, kc, vc, D, static_cast<int>(a->cache_rows), ctx->tail_k, ctx->tail_v, D, S,
+    RUN(0, 4.0 * S * lk_self * D, flash_attn_bf16(qkv, 3 * D, S, H, kc, vc, D, static_cast<int>(a->cache_rows), ctx->tail_k, ctx->tail_v, D, S,
                         nseg, seg_start, seg_rows, seg_src, attn, D, scale, st));
-    RUN(gemm_bf16(attn, D, w.o_w, D, w.o_b, x, D, S, D, D, MMPL_EPI_BIAS_GATE_RES, x, D, emod + 2 * D, 6 * D, fs, 0, st));
+    RUN(2, 2.0 * S * D * D, gemm_bf16(attn, D, w.o_w, D, w.o_b, x, D, S, D, D, MMPL_EPI_BIAS_GATE_RES, x, D, emod + 2 * D, 6 * D, fs, 0, st));
     // cross-attention (causal_model.py:314; model.py:159-194)
-    RUN(ln_affine(x, D, xm, D, S, D, c.eps, w.norm3_w, w.norm3_b, st));
-    RUN(gemm_bf16(xm, D, w.cq_w, D, w.cq_b, qkv, D, S, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
-    RUN(rmsnorm(qkv, D, qkv, D, S, D, w.cnorm_q, c.eps, st));
+    RUN(3, 4.0 * S * D, ln_affine(x, D, xm, D, S, D, c.eps, w.norm3_w, w.norm3_b, st));
+    RUN(2, 2.0 * S * D * D, gemm_bf16(xm, D, w.cq_w, D, w.cq_b, qkv, D, S, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+    RUN(3, 4.0 * S * D, rmsnorm(qkv, D, qkv, D, S, D, w.cnorm_q, c.eps, st));
     if (!a->cross_init) {
-      RUN(gemm_bf16(ctx->ctx_e, D, w.ck_w, D, w.ck_b, a->cross_k[l], D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
-      RUN(rmsnorm(a->cross_k[l], D, a->cross_k[l], D, T, D, w.cnorm_k, c.eps, st));
-      RUN(gemm_bf16(ctx->ctx_e, D, w.cv_w, D, w.cv_b, a->cross_v[l], D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+      RUN(2, 2.0 * T * D * D, gemm_bf16(ctx->ctx_e, D, w.ck_w, D, w.ck_b, a->cross_k[l], D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+      RUN(3, 4.0 * T * D, rmsnorm(a->cross_k[l], D, a->cross_k[l], D, T, D, w.cnorm_k, c.eps, st));
+      RUN(2, 2.0 * T * D * D, gemm_bf16(ctx->ctx_e, D, w.cv_w, D, w.cv_b, a->cross_v[l], D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
     }
-    RUN(flash_attn_bf16(qkv, D, S, H, a->cross_k[l], a->cross_v[l], D, T, nullptr, nullptr, 0, 0, 1, &cross_start,
+    RUN(1, 4.0 * S * T * D, flash_attn_bf16(qkv, D, S, H, a->cross_k[l], a->cross_v[l], D, T, nullptr, nullptr, 0, 0, 1, &cross_start,
                         &cross_rows, nullptr, attn, D, scale, st));
-    RUN(gemm_bf16(attn, D, w.co_w, D, w.co_b, x, D, S, D, D, MMPL_EPI_BIAS_RES, x, D, nullptr, 0, 0, 0, st));
+    RUN(2, 2.0 * S * D * D, gemm_bf16(attn, D, w.co_w, D, w.co_b, x, D, S, D, D, MMPL_EPI_BIAS_RES, x, D, nullptr, 0, 0, 0, st));
     // feed-forward (causal_model.py:316-322)
-    RUN(ln_modulate(x, D, xm, D, S, D, c.eps, emod + 3 * D, emod + 4 * D, 6 * D, fs, st));
-    RUN(gemm_bf16(xm, D, w.ffn0_w, D, w.ffn0_b, hbuf, Fd, S, Fd, D, MMPL_EPI_BIAS_GELU, nullptr, 0, nullptr, 0, 0, 0, st));
-    RUN(gemm_bf16(hbuf, Fd, w.ffn2_w, Fd, w.ffn2_b, x, D, S, D, Fd, MMPL_EPI_BIAS_GATE_RES, x, D, emod + 5 * D, 6 * D, fs, 0, st));
+    RUN(3, 4.0 * S * D, ln_modulate(x, D, xm, D, S, D, c.eps, emod + 3 * D, emod + 4 * D, 6 * D, fs, st));
+    RUN(2, 2.0 * S * D * Fd, gemm_bf16(xm, D, w.ffn0_w, D, w.ffn0_b, hbuf, Fd, S, Fd, D, MMPL_EPI_BIAS_GELU, nullptr, 0, nullptr, 0, 0, 0, st));
+    RUN(2, 2.0 * S * D * Fd, gemm_bf16(hbuf, Fd, w.ffn2_w, Fd, w.ffn2_b, x, D, S, D, Fd, MMPL_EPI_BIAS_GATE_RES, x, D, emod + 5 * D, 6 * D, fs, 0, st));
   }
 
   // head + unpatchify (+ flow -> x0) (causal_model.py:346-357, 889-892, 1094-1117; wan_wrapper.py:172-196)
-  RUN(modulation_add(g.head_mod, ctx->e, D, 0, ehead, F, 2, D, st));
-  RUN(ln_modulate(x, D, xm, D, S, D, c.eps, ehead, ehead + D, 2 * D, fs, st));
-  RUN(gemm_bf16(xm, D, g.head_w, D, g.head_b, ctx->hout, PO, S, PO, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
-  RUN(unpatchify_x0(ctx->hout, PO, a->latents, a->lat_stride_f, a->lat_stride_c, a->sigma, a->flow, a->x0, F, c.out_dim,
+  RUN(3, 0.0, modulation_add(g.head_mod, ctx->e, D, 0, ehead, F, 2, D, st));
+  RUN(3, 4.0 * S * D, ln_modulate(x, D, xm, D, S, D, c.eps, ehead, ehead + D, 2 * D, fs, st));
+  RUN(2, 2.0 * S * D * PO, gemm_bf16(xm, D, g.head_w, D, g.head_b, ctx->hout, PO, S, PO, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+  RUN(3, 6.0 * S * PO, unpatchify_x0(ctx->hout, PO, a->latents, a->lat_stride_f, a->lat_stride_c, a->sigma, a->flow, a->x0, F, c.out_dim,
                     a->lat_h, a->lat_w, st));
   return MMPL_OK;
 }

@@ -15,6 +15,9 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # the oracle runs as plain fp32 torch ops on the GPU in some parity tests: no TF32 shortcuts
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -108,7 +108,9 @@ def test_ln_modulate_and_affine(S, D, frames):
     fs = S // frames
     got = ops.ln_modulate(x, e[:, 0], e[:, 1], fs)
     ref = O.modulate(O.layer_norm(x, 1e-6), e[:, 0], e[:, 1], fs)
-    _report("ln_modulate", got, ref, atol=1e-6, rtol=8e-3)
+    # bf16(bf16(n)*s)+b: a 1-ulp flip of an intermediate (fp32 reduction order) can move the result by 2 ulp
+    _report("ln_modulate", got, ref, atol=1e-6, rtol=1.6e-2)
+    assert (got == ref).float().mean().item() > 0.9999
     w, b = _rand(D, seed=3), _rand(D, seed=4)
     _report("ln_affine", ops.ln_affine(x, w, b), O.layer_norm(x, 1e-6, w, b), atol=1e-6, rtol=8e-3)
 
@@ -142,18 +144,18 @@ def test_qk_norm_rope_kv(D, H, grid, frame_pos, kv_row):
     v_ref = v_in.clone()
     q_out = ops.qk_norm_rope_kv(q_in, k_in, v_in, wq, wk, table, kc, vc, (gh, gw), frame_pos, kv_row, q_out=q_in)
     assert q_out.data_ptr() == qkv.data_ptr()
-    _report("roped q", q_out, q_ref, atol=1e-6, rtol=8e-3)
+    _report("roped q", q_out, q_ref, atol=1e-6, rtol=1.6e-2)
     fs = gh * gw
     written = torch.zeros(rows, dtype=torch.bool, device=DEV)
     for i, r0 in enumerate(kv_row):
-        _report(f"cache k frame {i}", kc[r0:r0 + fs], k_ref[i * fs:(i + 1) * fs], atol=1e-6, rtol=8e-3)
+        _report(f"cache k frame {i}", kc[r0:r0 + fs], k_ref[i * fs:(i + 1) * fs], atol=1e-6, rtol=1.6e-2)
         assert torch.equal(vc[r0:r0 + fs], v_ref[i * fs:(i + 1) * fs]), "v rows must be copied bit-exactly"
         written[r0:r0 + fs] = True
     assert (kc[~written] == 0).all() and (vc[~written] == 0).all(), "rows outside the write window were touched"
     # the fraction of bit-identical elements should be overwhelming (only fp32 reduction order differs)
     same = (q_out == q_ref).float().mean().item()
     print("bit-identical roped q fraction:", same)
-    assert same > 0.99
+    assert same > 0.9999
 
 
 def test_time_embedding_pieces():

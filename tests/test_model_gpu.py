@@ -1,0 +1,203 @@
+"""Model- and pipeline-level parity of the CUDA path (through the C ABI: mmpl_forward) on the GPU:
+  * against golden vectors recorded from the unmodified reference (tests/golden/*.pt, oracle/make_golden.py),
+  * against the oracle restatement on identical inputs,
+  * at BASELINE.json's full cfg2 size through size-independent properties (index recurrence, rewrite
+    idempotence, cache rows outside the written window untouched).
+Tolerances (bf16 activations, per denoising step): stated next to each assert; they are calibrated against the
+oracle-vs-reference distance measured on CPU (tests/test_oracle_golden.py prints it)."""
+import types
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import causal_wan_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+DEV = "cuda"
+
+
+def _synth_inputs(cfg, frames, lat_h, lat_w, noise_seed=0, prompt_seed=1):
+    g0 = torch.Generator().manual_seed(noise_seed)
+    g1 = torch.Generator().manual_seed(prompt_seed)
+    noise = torch.randn(1, frames, cfg.in_dim, lat_h, lat_w, generator=g0).to(torch.bfloat16)
+    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=g1).to(torch.bfloat16)
+    return noise, prompt
+
+
+def build_pipeline(cfg, weights, prompt, steps=(1000, 750, 500, 250), nfpb=3, shift=5.0, model_cls=None):
+    from mmpl_b200.causal_model import CausalWanModel
+    from mmpl_b200.pipeline import CausalInferencePipeline
+    from mmpl_b200.wan_wrapper import WanDiffusionWrapper
+    model = (model_cls or CausalWanModel)(
+        text_len=cfg.text_len, in_dim=cfg.in_dim, dim=cfg.dim, ffn_dim=cfg.ffn_dim, freq_dim=cfg.freq_dim,
+        text_dim=cfg.text_dim, out_dim=cfg.out_dim, num_heads=cfg.num_heads, num_layers=cfg.num_layers, eps=cfg.eps)
+    model.load_state_dict(weights, strict=True)
+    model = model.to(device=DEV, dtype=torch.bfloat16).eval().requires_grad_(False)
+    gen = WanDiffusionWrapper(model=model, timestep_shift=shift)
+
+    class FakeText(torch.nn.Module):
+        def forward(self, text_prompts):
+            return {"prompt_embeds": prompt.to(DEV)}
+
+    class FakeVAE(torch.nn.Module):
+        def decode_to_pixel(self, latents, use_cache=False):
+            return latents
+
+    args = types.SimpleNamespace(denoising_step_list=list(steps), warp_denoising_step=True, independent_first_frame=False,
+                                 context_noise=0, num_frame_per_block=nfpb, model_kwargs={})
+    return CausalInferencePipeline(args, torch.device(DEV), generator=gen, text_encoder=FakeText(), vae=FakeVAE())
+
+
+def run_with_trace(pipe, noise, eps_list=None):
+    """Runs pipe.inference recording, per generator call, (current_start, timestep, end indices after the call, x0).
+    If eps_list is given, torch.randn_like replays those tensors (the golden run's CPU noise)."""
+    trace, x0s = [], []
+
+    def hook(mod, args, kwargs, out):
+        kv = kwargs["kv_cache"]
+        trace.append(dict(current_start=int(kwargs["current_start"]), timestep=float(kwargs["timestep"].flatten()[0]),
+                          global_end=int(kv[0]["global_end_index"].item()), local_end=int(kv[0]["local_end_index"].item()),
+                          all_equal=all(int(d["global_end_index"].item()) == int(kv[0]["global_end_index"].item())
+                                        and int(d["local_end_index"].item()) == int(kv[0]["local_end_index"].item()) for d in kv)))
+        x0s.append(out[1][0].clone())
+
+    h = pipe.generator.register_forward_hook(hook, with_kwargs=True)
+    orig = torch.randn_like
+    it = iter(eps_list) if eps_list is not None else None
+    if it is not None:
+        torch.randn_like = lambda x, *a, **k: next(it).to(device=x.device, dtype=x.dtype).reshape(x.shape)
+    try:
+        _, latents = pipe.inference(noise=noise.to(DEV), text_prompts=["synthetic"], return_latents=True)
+    finally:
+        torch.randn_like = orig
+        h.remove()
+    return trace, x0s, latents[0]
+
+
+def _cmp(name, got, ref, max_abs, min_cos):
+    g, r = got.float().cpu(), ref.float().cpu()
+    err = (g - r).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
+    print(f"{name}: max_abs={err:.4g} cos={cos:.6f} (|ref| mean {r.abs().mean().item():.3g})")
+    assert torch.isfinite(g).all(), f"{name}: non-finite values"
+    assert err <= max_abs and cos >= min_cos, f"{name}: max_abs={err:.4g} (tol {max_abs}) cos={cos:.6f} (tol {min_cos})"
+
+
+def _check_golden(fix_name, max_abs, min_cos):
+    fix = torch.load(GOLDEN / fix_name, weights_only=False)
+    cfg = O.WanConfig(**fix["cfg"])
+    w = O.make_weights(cfg, fix["weight_seed"])
+    noise, prompt = _synth_inputs(cfg, fix["frames"], fix["lat_h"], fix["lat_w"])
+    pipe = build_pipeline(cfg, w, prompt, fix["steps"], fix["nfpb"])
+    pipe.generator.model.launch_count(reset=True)
+    trace, x0s, latents = run_with_trace(pipe, noise, fix["eps"])
+    assert pipe.generator.model.launch_count() > 0, "no native kernels were launched"
+    # bit-exact: call schedule and cache indices
+    assert len(trace) == len(fix["trace"])
+    for got, ref in zip(trace, fix["trace"]):
+        assert got["current_start"] == ref["current_start"]
+        assert got["timestep"] == ref["timestep"]
+        assert (got["global_end"], got["local_end"]) == (ref["global_end"], ref["local_end"])
+        assert got["all_equal"]
+    # per-step latents (x0 prediction of every denoising call) and final output
+    for i, (g, r) in enumerate(zip(x0s, fix["x0"])):
+        _cmp(f"{fix_name} call {i} x0 (t={trace[i]['timestep']:.1f})", g, r, max_abs, min_cos)
+    _cmp(f"{fix_name} final latents", latents, fix["latents"], max_abs, min_cos)
+    return fix, pipe
+
+
+def test_golden_tiny_pipeline():
+    """2-layer, dim-256 model, 6 frames in 2 chunks, 10 generator calls. Tolerance: max-abs 0.0625, cosine 0.9999 per
+    step (oracle-vs-reference on CPU: max-abs 0.0156, cosine 0.999999)."""
+    fix, pipe = _check_golden("causal_tiny.pt", max_abs=0.0625, min_cos=0.9999)
+    kv = pipe.kv_cache1
+    _cmp("layer0 K cache", kv[0]["k"][0], fix["kv_k0"], 0.0625, 0.9999)
+    _cmp("layer0 V cache", kv[0]["v"][0], fix["kv_v0"], 0.0625, 0.9999)
+    _cmp("last layer K cache", kv[-1]["k"][0], fix["kv_k_last"], 0.125, 0.9995)
+    _cmp("layer0 cross K", pipe.crossattn_cache[0]["k"][0], fix["cross_k0"], 0.0625, 0.9999)
+    # rows never written stay zero (window exactness)
+    written = fix["trace"][-1]["local_end"]
+    assert (kv[0]["k"][0, written:] == 0).all() and (kv[0]["v"][0, written:] == 0).all()
+    assert all(c["is_init"] for c in pipe.crossattn_cache)
+
+
+def test_golden_cfg1_pipeline():
+    """BASELINE.json configs[0]: Wan-1.3B dims, 30 blocks, 1 chunk x 3 frames at 30x52, 4 steps + context pass.
+    Tolerance per step: max-abs 0.25, cosine 0.999 (30 blocks of bf16 rounding; values are O(1))."""
+    _check_golden("causal_cfg1.pt", max_abs=0.25, min_cos=0.999)
+
+
+def test_forward_matches_oracle_and_rewrite_is_idempotent():
+    """One mid-size forward (dim 512, 4 heads, 3 blocks, 3 frames of 16x20 latents) against the oracle run on the
+    same device, then the same call again: the second call must rewrite the same rows and return identical output."""
+    from mmpl_b200.causal_model import CausalWanModel
+    cfg = O.WanConfig(dim=512, ffn_dim=1024, num_heads=4, num_layers=3, text_dim=128, text_len=64)
+    w = O.make_weights(cfg, seed=3)
+    noise, prompt = _synth_inputs(cfg, 6, 16, 20)
+    model = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
+                           num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+    model.load_state_dict(w)
+    model = model.to(DEV, torch.bfloat16).eval()
+    fs = 8 * 10
+    rows = 6 * fs + 40
+    kv = [{"k": torch.zeros(1, rows, 4, 128, dtype=torch.bfloat16, device=DEV), "v": torch.zeros(1, rows, 4, 128, dtype=torch.bfloat16, device=DEV),
+           "global_end_index": torch.tensor([0], device=DEV), "local_end_index": torch.tensor([0], device=DEV)} for _ in range(3)]
+    cross = [{"k": None, "v": None, "is_init": False} for _ in range(3)]
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    okv, ocross = O.new_caches(cfg, rows, device=DEV)
+    outs = []
+    for chunk, t_val in ((0, 1000.0), (0, 625.0), (1, 937.5)):
+        x = noise[:, chunk * 3:(chunk + 1) * 3].to(DEV)
+        t = torch.full((1, 3), t_val, device=DEV)
+        flow = model(x.permute(0, 2, 1, 3, 4), t=t, context=prompt.to(DEV), seq_len=32760, kv_cache=kv, crossattn_cache=cross,
+                     current_start=chunk * 3 * fs)
+        ref = O.model_forward(cfg, wd, x[0].permute(1, 0, 2, 3), t[0], prompt[0].to(DEV), okv, ocross, chunk * 3 * fs)
+        _cmp(f"flow chunk {chunk} t={t_val}", flow[0], ref, 0.0625, 0.9999)
+        assert int(kv[0]["local_end_index"].item()) == okv[0].local_end_index == (chunk + 1) * 3 * fs
+        assert int(kv[2]["global_end_index"].item()) == okv[2].global_end_index
+        outs.append(flow.clone())
+    for i in range(3):
+        _cmp(f"K cache layer {i}", kv[i]["k"][0], okv[i].k, 0.125, 0.9995)
+        assert (kv[i]["k"][0, 6 * fs:] == 0).all()
+    # idempotence: same chunk, same timestep again -> same rows rewritten, bit-identical output
+    snap = kv[1]["k"].clone()
+    x = noise[:, 3:6].to(DEV)
+    flow2 = model(x.permute(0, 2, 1, 3, 4), t=torch.full((1, 3), 937.5, device=DEV), context=prompt.to(DEV), seq_len=32760,
+                  kv_cache=kv, crossattn_cache=cross, current_start=3 * fs)
+    assert torch.equal(flow2, outs[2]) and torch.equal(kv[1]["k"], snap)
+
+
+def test_cfg2_full_size_properties():
+    """BASELINE.json configs[1] shape (21 frames, 60x104 latents, 3-frame chunks, 32760-row cache) on a 2-block
+    Wan-1.3B-width model: index recurrence over all 35 calls, full cache fill, finite outputs, and the attention
+    window of the last chunk equals the whole cache."""
+    cfg = O.WanConfig(num_layers=2)
+    w = O.make_weights(cfg, seed=5)
+    noise, prompt = _synth_inputs(cfg, 21, 60, 104)
+    pipe = build_pipeline(cfg, w, prompt)
+    trace, x0s, latents = run_with_trace(pipe, noise)
+    assert len(trace) == 35
+    for i, tr in enumerate(trace):
+        chunk = i // 5
+        assert tr["current_start"] == chunk * 4680
+        assert tr["global_end"] == tr["local_end"] == (chunk + 1) * 4680 and tr["all_equal"]
+    assert trace[-1]["local_end"] == 32760 == pipe.kv_cache1[0]["k"].shape[1]
+    assert torch.isfinite(latents.float()).all() and latents.float().abs().mean() > 0
+    steps = [round(t["timestep"], 2) for t in trace[:5]]
+    assert steps == [1000.0, 937.5, 833.33, 625.0, 0.0]
+    # last chunk against the oracle on the same device: KV length 32760
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    okv, ocross = O.new_caches(cfg, 32760, device=DEV)
+    for i in range(2):
+        okv[i].k.copy_(pipe.kv_cache1[i]["k"][0])
+        okv[i].v.copy_(pipe.kv_cache1[i]["v"][0])
+        okv[i].global_end_index = okv[i].local_end_index = 32760
+    x = latents[18:21]
+    t = torch.zeros(3, device=DEV)
+    ref = O.model_forward(cfg, wd, x.permute(1, 0, 2, 3), t, prompt[0].to(DEV), okv, ocross, 18 * 1560)
+    flow, _ = pipe.generator(noisy_image_or_video=x[None], conditional_dict={"prompt_embeds": prompt.to(DEV)},
+                             timestep=torch.zeros(1, 3, device=DEV), kv_cache=pipe.kv_cache1,
+                             crossattn_cache=pipe.crossattn_cache, current_start=18 * 1560)
+    _cmp("cfg2 last-chunk flow (Lkv=32760)", flow[0], ref.permute(1, 0, 2, 3), 0.0625, 0.9999)
