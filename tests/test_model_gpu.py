@@ -113,9 +113,10 @@ def test_golden_tiny_pipeline():
     step (oracle-vs-reference on CPU: max-abs 0.0156, cosine 0.999999)."""
     fix, pipe = _check_golden("causal_tiny.pt", max_abs=0.0625, min_cos=0.9999)
     kv = pipe.kv_cache1
-    _cmp("layer0 K cache", kv[0]["k"][0], fix["kv_k0"], 0.0625, 0.9999)
-    _cmp("layer0 V cache", kv[0]["v"][0], fix["kv_v0"], 0.0625, 0.9999)
-    _cmp("last layer K cache", kv[-1]["k"][0], fix["kv_k_last"], 0.125, 0.9995)
+    rows = fix["cache_rows"]  # the golden run used a short cache; the pipeline allocates the reference's 32760 rows
+    _cmp("layer0 K cache", kv[0]["k"][0, :rows], fix["kv_k0"], 0.0625, 0.9999)
+    _cmp("layer0 V cache", kv[0]["v"][0, :rows], fix["kv_v0"], 0.0625, 0.9999)
+    _cmp("last layer K cache", kv[-1]["k"][0, :rows], fix["kv_k_last"], 0.125, 0.9995)
     _cmp("layer0 cross K", pipe.crossattn_cache[0]["k"][0], fix["cross_k0"], 0.0625, 0.9999)
     # rows never written stay zero (window exactness)
     written = fix["trace"][-1]["local_end"]
@@ -125,8 +126,9 @@ def test_golden_tiny_pipeline():
 
 def test_golden_cfg1_pipeline():
     """BASELINE.json configs[0]: Wan-1.3B dims, 30 blocks, 1 chunk x 3 frames at 30x52, 4 steps + context pass.
-    Tolerance per step: max-abs 0.25, cosine 0.999 (30 blocks of bf16 rounding; values are O(1))."""
-    _check_golden("causal_cfg1.pt", max_abs=0.25, min_cos=0.999)
+    Tolerance per step: max-abs 0.125, cosine 0.9999 (measured: 0.031 / 0.99999, the same distance the bf16 oracle has
+    from the reference on CPU)."""
+    _check_golden("causal_cfg1.pt", max_abs=0.125, min_cos=0.9999)
 
 
 def test_forward_matches_oracle_and_rewrite_is_idempotent():
