@@ -1,3 +1,4 @@
+from .causal_fps_inference import CausalFPSInferencePipeline
 from .causal_inference import CausalInferencePipeline
 
-__all__ = ["CausalInferencePipeline"]
+__all__ = ["CausalInferencePipeline", "CausalFPSInferencePipeline"]

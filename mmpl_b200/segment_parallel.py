@@ -1,0 +1,107 @@
+"""MMPL segment-parallel long-video generation over torch.distributed.
+
+The reference runs one pipeline replica per GPU in Python threads and hands the anchor latents of segment k to segment
+k+1 through a `.pt` file that the consumer polls every second (Wan_fps_inference_parallel_4gpu_20s.py:176-261;
+pipeline/casual_fps_inference.py:380-383). Here every GPU is one process (torchrun), segment k runs on rank k % G, and
+the hand-off is a point-to-point message on the communicator (NCCL over NVLink on GPUs: the send is enqueued on the
+compute stream right after the anchor stage, so the producer continues with its next stage immediately; gloo in the CPU
+tests). The path has no other exchange: each rank holds a full replica and its own caches.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+T2V_ANCHOR_SHAPE = (1, 8, 16, 60, 104)   # frame 0 + stage-1 frames [2,3,10,11,12,19,20]  (1.6 MB bf16)
+I2V_ANCHOR_SHAPE = (1, 3, 16, 60, 104)   # frames 0, 19, 20                               (0.6 MB bf16)
+
+
+def segments_of_rank(rank: int, world: int, num_segments: int) -> List[int]:
+    """Round-robin placement: rank r runs segments r, r+G, r+2G, ... (the 5-60s driver's rotation, :231-238)."""
+    return list(range(rank, num_segments, world))
+
+
+def producer_of(segment: int, world: int) -> int:
+    return segment % world
+
+
+def default_segment_connect(anchors: torch.Tensor) -> torch.Tensor:
+    """Stand-in for the reference's "segment connect" (decode anchors with the VAE, take pixel frames 8:13, re-encode,
+    keep the first 2 latents; Wan_fps_inference_parallel_4gpu_20s.py:191-205): the VAE is outside the hot path and its
+    weights are absent, so the last two anchor latents (frames 19, 20 of the previous segment) are used directly."""
+    return anchors[:, -2:].contiguous()
+
+
+class AnchorChannel:
+    """Point-to-point hand-off of one segment's anchor latents to the rank that runs the next segment."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._local: Dict[int, torch.Tensor] = {}
+        self._pending = []
+        self.bytes_sent = 0
+
+    def send(self, anchors: torch.Tensor, segment: int) -> None:
+        dst = producer_of(segment + 1, self.world)
+        payload = anchors.contiguous()
+        self.bytes_sent += payload.numel() * payload.element_size()
+        if dst == self.rank:
+            self._local[segment + 1] = payload.clone()
+            return
+        self._pending.append((dist.isend(payload, dst=dst, group=self.group, tag=segment + 1), payload))
+
+    def recv(self, segment: int, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Tensor:
+        src = producer_of(segment - 1, self.world)
+        if src == self.rank:
+            return self._local.pop(segment)
+        buf = torch.empty(tuple(shape), dtype=dtype, device=device)
+        dist.recv(buf, src=src, group=self.group, tag=segment)
+        return buf
+
+    def flush(self) -> None:
+        for work, _ in self._pending:
+            work.wait()
+        self._pending.clear()
+
+
+class SegmentParallelRunner:
+    """Runs `num_segments` 21-frame segments of one long video across the ranks of the group.
+
+    `pipeline` is a CausalFPSInferencePipeline (or anything with `inference(noise, text_prompts, initial_latent=...,
+    return_latents=True)` and a settable `anchor_sink`). `make_noise(segment)` returns that segment's noise tensor."""
+
+    def __init__(self, pipeline, channel: Optional[AnchorChannel] = None, anchor_shape: Sequence[int] = T2V_ANCHOR_SHAPE,
+                 connect: Callable[[torch.Tensor], torch.Tensor] = default_segment_connect):
+        self.pipeline = pipeline
+        self.channel = channel or AnchorChannel()
+        self.anchor_shape = tuple(anchor_shape)
+        self.connect = connect
+        self.log: List[tuple] = []
+
+    def run(self, make_noise: Callable[[int], torch.Tensor], text_prompts: List[str], num_segments: int) -> Dict[int, torch.Tensor]:
+        ch = self.channel
+        outputs: Dict[int, torch.Tensor] = {}
+        for seg in segments_of_rank(ch.rank, ch.world, num_segments):
+            noise = make_noise(seg)
+            initial = None
+            if seg > 0:
+                anchors = ch.recv(seg, (noise.shape[0],) + self.anchor_shape[1:3] + tuple(noise.shape[3:]), noise.dtype, noise.device)
+                initial = self.connect(anchors)
+                self.log.append(("recv", seg, producer_of(seg - 1, ch.world)))
+            has_next = seg + 1 < num_segments
+
+            def sink(payload, seg=seg, has_next=has_next):
+                if has_next:
+                    ch.send(payload, seg)
+                    self.log.append(("send", seg, producer_of(seg + 1, ch.world)))
+
+            self.pipeline.anchor_sink = sink
+            _, latents = self.pipeline.inference(noise=noise, text_prompts=text_prompts, initial_latent=initial,
+                                                 return_latents=True)
+            outputs[seg] = latents
+        ch.flush()
+        return outputs

@@ -112,6 +112,66 @@ def make_cfg1():
     print("cfg1:", len(r["trace"]), "calls,", f"{r['seconds']:.2f}s", r["trace"])
 
 
+def make_fps():
+    """CausalFPSWanModel (wan/modules/causal_fps_model.py) driven through the four t2v stages of the MMPL schedule,
+    one forward per stage (plus a repeat of the anchor stage), with the pipeline's attention_vis_index edits between
+    stages (pipeline/casual_fps_inference.py:297-325). Tiny width (dim 256, 2 blocks) but the full 60x104 latent, because
+    the reference hard-codes 1560 tokens per frame in this branch. Outputs are stored sub-sampled (every 4th latent
+    row/column) together with the rows of the cache that changed."""
+    import importlib
+    ref_shim.load()
+    fps_mod = importlib.import_module("wan.modules.causal_fps_model")
+    attn_mod = importlib.import_module("wan.modules.attention")
+    cfg = TINY
+    w = O.make_weights(cfg, seed=7)
+    model = fps_mod.CausalFPSWanModel(model_type="t2v", patch_size=cfg.patch_size, text_len=cfg.text_len, in_dim=cfg.in_dim,
+                                      dim=cfg.dim, ffn_dim=cfg.ffn_dim, freq_dim=cfg.freq_dim, text_dim=cfg.text_dim,
+                                      out_dim=cfg.out_dim, num_heads=cfg.num_heads, num_layers=cfg.num_layers, eps=cfg.eps)
+    model.load_state_dict(w, strict=True)
+    model = model.to(torch.bfloat16).eval().requires_grad_(False)
+    fs, rows = 1560, 15 * 1560
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(1, 21, 16, 60, 104, generator=g).to(torch.bfloat16)
+    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=g).to(torch.bfloat16)
+    kv = [{"k": torch.zeros(1, rows, cfg.num_heads, 128, dtype=torch.bfloat16), "v": torch.zeros(1, rows, cfg.num_heads, 128, dtype=torch.bfloat16),
+           "global_end_index": torch.tensor([0]), "local_end_index": torch.tensor([0]), "attention_vis_index": []}
+          for _ in range(cfg.num_layers)]
+    cross = [{"k": torch.zeros(1, cfg.text_len, cfg.num_heads, 128, dtype=torch.bfloat16),
+              "v": torch.zeros(1, cfg.text_len, cfg.num_heads, 128, dtype=torch.bfloat16), "is_init": False} for _ in range(cfg.num_layers)]
+    stages = [[0, 1], [2, 3, 10, 11, 12, 19, 20], [2, 3, 10, 11, 12, 19, 20], [4, 5, 6, 7, 8, 9], [13, 14, 15, 16, 17, 18]]
+    tvals = [999.0, 640.0, 0.0, 320.0, 87.0]
+    calls = []
+    for si, (frames, tv) in enumerate(zip(stages, tvals)):
+        if si == 3:
+            for blk in kv:
+                for val in (31200, 29640):
+                    if val in blk["attention_vis_index"]:
+                        blk["attention_vis_index"].remove(val)
+        if si == 4:
+            for blk in kv:
+                for val in (31200, 29640):
+                    if val not in blk["attention_vis_index"]:
+                        blk["attention_vis_index"].append(val)
+        before = kv[1]["k"][0].clone()
+        x = noise[:, frames]
+        t = torch.full((1, len(frames)), tv)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            flow = model(x.permute(0, 2, 1, 3, 4), t=t, context=prompt, seq_len=32760, kv_cache=kv, crossattn_cache=cross,
+                         current_start=[f * fs for f in frames], cache_start=[f * fs for f in frames])
+        changed = (kv[1]["k"][0] != before).flatten(1).any(dim=1)
+        changed_slots = sorted(set((changed.nonzero().flatten() // fs).tolist()))
+        calls.append(dict(frames=frames, t=tv, vis=sorted(kv[0]["attention_vis_index"]), changed_slots=changed_slots,
+                          flow_sub=flow[0].permute(1, 0, 2, 3)[:, :, ::4, ::4].clone(),
+                          flow_absmean=flow.float().abs().mean().item(),
+                          end_indices=(int(kv[0]["global_end_index"]), int(kv[0]["local_end_index"]))))
+        print(f"fps stage {si}: frames {frames} vis {calls[-1]['vis']} changed slots {changed_slots} {time.perf_counter() - t0:.1f}s")
+    fix = dict(kind="fps_model", cfg=cfg.__dict__, weight_seed=7, input_seed=11, calls=calls,
+               inputs_sha=digest([noise, prompt]),
+               kv_k_layer1_sub=kv[1]["k"][0, ::97].clone(), kv_v_layer0_sub=kv[0]["v"][0, ::97].clone())
+    torch.save(fix, GOLDEN / "fps_model_tiny.pt")
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     which = sys.argv[1:] or ["tiny", "cfg1"]
@@ -119,3 +179,5 @@ if __name__ == "__main__":
         make_tiny()
     if "cfg1" in which:
         make_cfg1()
+    if "fps" in which:
+        make_fps()

@@ -154,3 +154,55 @@ def build_reference_pipeline(ref, cfg, weights: dict, prompt_embeds: torch.Tenso
         "is_init": False,
     } for _ in range(cfg.num_layers)]
     return pipe
+
+
+def load_unipc():
+    """The reference's FlowUniPCMultistepScheduler (wan/utils/fm_solvers_unipc.py) with a minimal diffusers stub:
+    SchedulerMixin / ConfigMixin whose register_to_config stores the constructor arguments in `self.config`."""
+    load()
+    import functools
+    import importlib
+    import inspect
+
+    cu = sys.modules["diffusers.configuration_utils"]
+
+    class ConfigMixin:
+        def register_to_config(self, **kw):
+            if not hasattr(self, "config"):
+                self.config = types.SimpleNamespace()
+            for k, v in kw.items():
+                setattr(self.config, k, v)
+
+    def register_to_config(init):
+        @functools.wraps(init)
+        def wrapper(self, *args, **kwargs):
+            sig = inspect.signature(init)
+            bound = sig.bind(self, *args, **kwargs)
+            bound.apply_defaults()
+            self.config = types.SimpleNamespace(**{k: v for k, v in bound.arguments.items() if k != "self"})
+            init(self, *args, **kwargs)
+        return wrapper
+
+    cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+    sch = types.ModuleType("diffusers.schedulers")
+    sch.__path__ = []
+    su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+
+    class SchedulerMixin:
+        pass
+
+    class SchedulerOutput:
+        def __init__(self, prev_sample):
+            self.prev_sample = prev_sample
+
+    class KarrasDiffusionSchedulers(list):
+        pass
+
+    su.SchedulerMixin, su.SchedulerOutput = SchedulerMixin, SchedulerOutput
+    su.KarrasDiffusionSchedulers = [types.SimpleNamespace(name="stub")]
+    ut = types.ModuleType("diffusers.utils")
+    ut.deprecate = lambda *a, **k: None
+    ut.is_scipy_available = lambda: False
+    sys.modules.update({"diffusers.schedulers": sch, "diffusers.schedulers.scheduling_utils": su, "diffusers.utils": ut})
+    mod = importlib.import_module("wan.utils.fm_solvers_unipc")
+    return mod.FlowUniPCMultistepScheduler
