@@ -164,7 +164,7 @@ class CausalWanModel(nn.Module):
                                "(call .to(device='cuda', dtype=torch.bfloat16)); there is no CPU fallback")
         if self._ctx is not None and tokens > self._ctx_tokens:
             lib.mmpl_ctx_destroy(self._ctx)
-            self._ctx, self._bound_sig = None, None
+            self._ctx, self._bound_sig, self._rope_table = None, None, None
         if self._ctx is None:
             cap = max(tokens, 3 * 1560)
             cfg = _lib.ModelConfig(self.dim, self.ffn_dim, self.num_heads, self.num_layers, self.freq_dim, self.text_dim,
