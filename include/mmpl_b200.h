@@ -66,6 +66,9 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
                     int64_t ldo, float softmax_scale, void* stream);
 
+/* Tuning / test hook: force the number of KV chunks each attention unit is split into (0 = cost model). */
+int mmpl_attn_set_split(int split);
+
 /* bf16(bf16(bf16(LayerNorm(x)) * bf16(1 + scale_f)) + shift_f); shift/scale are [frames][mod_stride]
  * (causal_model.py:305,318; WanLayerNorm model.py:89-99). D in {256,512,1536,5120}. */
 int mmpl_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps,

@@ -121,6 +121,11 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                          seg_src, out, ldo, softmax_scale, static_cast<cudaStream_t>(stream)));
 }
 
+int mmpl_attn_set_split(int split) {
+  flash_attn_force_split(split);
+  return MMPL_OK;
+}
+
 int mmpl_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                      const void* scale, int64_t mod_stride, int rows_per_frame, void* stream) {
   COUNTED(ln_modulate(x, ldx, out, ldo, S, D, eps, shift, scale, mod_stride, rows_per_frame,

@@ -9,20 +9,48 @@
 // may also come from a second (K,V) pair, which is the "cat(gathered cache, new K/V)" of the last
 // MMPL stage (:254-264).
 //
-// One CTA = one head x two 128-row query tiles that ping-pong on the tensor pipe:
-//   warp 0      TMA producer (Q once; K and V tiles through 2-stage rings)
+// Work unit = one head x two 128-row query tiles that ping-pong on the tensor pipe, against T KV tiles
+// of 128 rows. The kernel is persistent; to balance the SMs every unit's KV range is cut into `split`
+// equal chunks ("pieces", split chosen by a cost model on the host) and CTA b runs pieces b, b+G, ...
+// Pieces are ordered (head, chunk, query pair), so the CTAs that run side by side read the same K/V tiles
+// and share them through L2. With split == 1 a piece is a whole unit and writes the normalised bf16
+// output directly; otherwise it writes its un-normalised fp32 O and (max, sum) to a workspace and
+// attn_combine_kernel merges the chunks. (cfg2: 228 units on 148 SMs = 1.54 waves of work; a
+// one-CTA-per-unit grid takes 2 full waves.)
+//   warp 0      TMA producer (Q per piece; K and V tiles through 2-stage rings)
 //   warp 1      MMA issuer:  S_q = Q_q K^T (SS),  O_q += P_q V (A = P from TMEM, B = V MN-major)
 //   warps 4-7   softmax for query tile 0 (thread = row), warps 8-11 for query tile 1
 // TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); bf16 P_q overwrites the
 // first 64 columns of S_q. O is rescaled lazily (only when the running max grows by > 2^8), by the
 // softmax warps themselves.
+#include <cstdlib>
+
 #include "host_util.h"
 #include "mmpl_b200.h"
 #include "ptx.cuh"
 
-namespace mmpl {
+#ifndef MMPL_ATTN_NS
+#define MMPL_ATTN_NS prod
+#define MMPL_ATTN_PROD 1
+#endif
+#ifndef MMPL_ATTN_HALVES
+#define MMPL_ATTN_HALVES 0
+#endif
 
+namespace mmpl {
+namespace MMPL_ATTN_NS {
+
+// 12 warps: warpgroup 0 = control (warp 0 TMA producer, warp 1 MMA issuer, 2 idle), warpgroups 1 and 2 = softmax of
+// query tile 0 / 1. setmaxnreg moves registers from the control warpgroup to the softmax warpgroups:
+// 128 x 96 + 256 x 200 = 63488 <= 384 x 168 (the launch allocation; exceeding it deadlocks setmaxnreg.inc). (ptxas bounds the code that follows each setmaxnreg by its value: with 56 registers
+// the control warps spilled their loop state and the MMA issue slowed down by ~25 %.)
 constexpr int kAttnThreads = 384;
+constexpr int kFirstSoftmaxWarp = 4;
+#ifndef MMPL_ATTN_CTRL_REGS
+#define MMPL_ATTN_CTRL_REGS 96
+#define MMPL_ATTN_SOFTMAX_REGS 200
+#endif
+constexpr int kAttnThreadsUnused = 320;  // warps 0,1 = TMA, MMA; warps 2-5 / 6-9 = softmax of query tile 0 / 1
 constexpr int kQTile = 128;
 constexpr int kKVTile = 128;
 constexpr int kHD = 128;
@@ -31,16 +59,80 @@ constexpr int kKVStages = 2;
 constexpr int kAttnSmem = 4 * kBoxBytes /*Q*/ + kKVStages * 2 * kBoxBytes /*K*/ +
                           kKVStages * 2 * kBoxBytes /*V*/ + 1024 + 256;
 constexpr int kMaxSeg = 8;
+constexpr int kUnitRows = 2 * kQTile;
 
 struct AttnParams {
-  int Lq;
+  int Lq, H;
+  int QP;         // query-tile pairs per head
+  int T;          // KV tiles per unit
+  int split;      // KV chunks per unit (= workspace slots per unit)
+  int n_pieces;   // U * split
   __nv_bfloat16* out;
   int64_t ldo;
   float scale_log2;
+  float* part_o;   // [U][P][256][128] un-normalised O of partial pieces
+  float* part_ml;  // [U][P][256][2]   (running max in the scaled log2 domain, running sum)
   int nseg;
   int seg_start[kMaxSeg];
   int seg_rows[kMaxSeg];
   int seg_src[kMaxSeg];
+};
+
+// Piece pi (ordered head-major, then KV chunk, then query pair) -> unit, head, first tile, tile count, chunk.
+struct Piece { int u, head, q_row0, t0, n, chunk; };
+__device__ __forceinline__ Piece piece_info(const AttnParams& p, int pi) {
+  Piece pc;
+  const int per_head = p.split * p.QP;
+  pc.head = pi / per_head;
+  const int r = pi - pc.head * per_head;
+  pc.chunk = r / p.QP;
+  const int qp = r - pc.chunk * p.QP;
+  pc.u = pc.head * p.QP + qp;
+  pc.q_row0 = qp * (2 * kQTile);
+  pc.t0 = static_cast<int>(static_cast<long long>(pc.chunk) * p.T / p.split);
+  pc.n = static_cast<int>(static_cast<long long>(pc.chunk + 1) * p.T / p.split) - pc.t0;
+  return pc;
+}
+
+// Select over the (at most 8) segment parameters without indexing the kernel-parameter arrays dynamically
+// (a dynamic index would make the compiler copy them to local memory).
+__device__ __forceinline__ int seg_field(const int (&a)[kMaxSeg], int i) {
+  int r = a[0];
+#pragma unroll
+  for (int k = 1; k < kMaxSeg; ++k) r = (i == k) ? a[k] : r;
+  return r;
+}
+
+// Walks the KV tiles of a unit in order: source, first row and number of valid rows of the current tile.
+struct TileIter {
+  int seg, src, row, rows_left;
+  __device__ __forceinline__ void load_seg(const AttnParams& p) {
+    src = seg_field(p.seg_src, seg);
+    row = seg_field(p.seg_start, seg);
+    rows_left = seg_field(p.seg_rows, seg);
+  }
+  __device__ __forceinline__ void init(const AttnParams& p, int j) {  // position on tile j of the unit
+    seg = 0;
+    load_seg(p);
+    while (seg < p.nseg - 1) {
+      const int nt = (rows_left + kKVTile - 1) / kKVTile;
+      if (j < nt) break;
+      j -= nt;
+      ++seg;
+      load_seg(p);
+    }
+    row += j * kKVTile;
+    rows_left -= j * kKVTile;
+  }
+  __device__ __forceinline__ int valid() const { return min(kKVTile, rows_left); }
+  __device__ __forceinline__ void next(const AttnParams& p) {
+    row += kKVTile;
+    rows_left -= kKVTile;
+    if (rows_left <= 0 && seg < p.nseg - 1) {
+      ++seg;
+      load_seg(p);
+    }
+  }
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -54,19 +146,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint8_t* smem_v = smem_k + kKVStages * 2 * kBoxBytes;     // [stage][hd half]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKVStages * 2 * kBoxBytes);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // 2
-  uint64_t* k_empty = bars + 3;            // 2
-  uint64_t* v_full = bars + 5;             // 2
-  uint64_t* v_empty = bars + 7;            // 2
-  uint64_t* s_full = bars + 9;             // 2 (per query tile)
-  uint64_t* p_full = bars + 11;            // 2
-  uint64_t* o_full = bars + 13;            // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_empty = bars + 1;            // 1
+  uint64_t* k_full = bars + 2;             // 2
+  uint64_t* k_empty = bars + 4;            // 2
+  uint64_t* v_full = bars + 6;             // 2
+  uint64_t* v_empty = bars + 8;            // 2
+  uint64_t* s_full = bars + 10;            // 2 (per query tile)
+  uint64_t* p_full = bars + 12;            // 4: [query tile][half of the KV tile]
+  uint64_t* o_full = bars + 16;            // 1
+  uint64_t* o_empty = bars + 17;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q_row0 = blockIdx.x * (2 * kQTile);
+  const int G = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -76,6 +169,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(q_full, 1);
+      mbar_init(q_empty, 1);
       for (int i = 0; i < kKVStages; ++i) {
         mbar_init(&k_full[i], 1);
         mbar_init(&k_empty[i], 1);
@@ -84,7 +178,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
-        mbar_init(&p_full[i], 4);
+        mbar_init(&p_full[2 * i], 4);
+        mbar_init(&p_full[2 * i + 1], 4);
+        mbar_init(&o_empty[i], 4);
       }
       mbar_init(o_full, 1);
       fence_mbar_init();
@@ -98,38 +194,39 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+  if (warp < kFirstSoftmaxWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MMPL_ATTN_CTRL_REGS));
     if (warp == 0 && lane == 0) {
       // -------------------------------------------------------- TMA producer
-      mbar_arrive_expect_tx(q_full, 4 * kBoxBytes);
-      for (int qt = 0; qt < 2; ++qt)
-        for (int hh = 0; hh < 2; ++hh)
-          tma_load_2d(smem_q + (qt * 2 + hh) * kBoxBytes, &map_q, q_full, head * kHD + hh * 64,
-                      q_row0 + qt * kQTile, kEvictFirst);
-      int j = 0;
-      for (int sg = 0; sg < p.nseg; ++sg) {
-        const CUtensorMap* mk = p.seg_src[sg] ? &map_k1 : &map_k0;
-        const CUtensorMap* mv = p.seg_src[sg] ? &map_v1 : &map_v0;
-        const int nt = (p.seg_rows[sg] + kKVTile - 1) / kKVTile;
-        for (int t = 0; t < nt; ++t, ++j) {
-          const int st = j & 1;
-          const uint32_t ph = (j >> 1) & 1;
-          const int row = p.seg_start[sg] + t * kKVTile;
+      int g = 0, piece = 0;
+      for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
+        const Piece pc = piece_info(p, pi);
+        const int t0 = pc.t0, n = pc.n, head = pc.head, q_row0 = pc.q_row0;
+        mbar_wait(q_empty, (piece & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, 4 * kBoxBytes);
+        for (int qt = 0; qt < 2; ++qt)
+          for (int hh = 0; hh < 2; ++hh)
+            tma_load_2d(smem_q + (qt * 2 + hh) * kBoxBytes, &map_q, q_full, head * kHD + hh * 64,
+                        q_row0 + qt * kQTile, kEvictFirst);
+        TileIter it;
+        it.init(p, t0);
+        for (int jj = 0; jj < n; ++jj, ++g, it.next(p)) {
+          const CUtensorMap* mk = it.src ? &map_k1 : &map_k0;
+          const CUtensorMap* mv = it.src ? &map_v1 : &map_v0;
+          const int st = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[st], 2 * kBoxBytes);
           for (int hh = 0; hh < 2; ++hh)
-            tma_load_2d(smem_k + (st * 2 + hh) * kBoxBytes, mk, &k_full[st], head * kHD + hh * 64, row, kEvictLast);
+            tma_load_2d(smem_k + (st * 2 + hh) * kBoxBytes, mk, &k_full[st], head * kHD + hh * 64, it.row, kEvictLast);
           mbar_wait(&v_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[st], 2 * kBoxBytes);
           for (int hh = 0; hh < 2; ++hh)
-            tma_load_2d(smem_v + (st * 2 + hh) * kBoxBytes, mv, &v_full[st], head * kHD + hh * 64, row, kEvictLast);
+            tma_load_2d(smem_v + (st * 2 + hh) * kBoxBytes, mv, &v_full[st], head * kHD + hh * 64, it.row, kEvictLast);
         }
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------- MMA issuer
-      int n_tiles = 0;
-      for (int sg = 0; sg < p.nseg; ++sg) n_tiles += (p.seg_rows[sg] + kKVTile - 1) / kKVTile;
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
       const uint32_t q_addr = smem_u32(smem_q);
@@ -148,88 +245,118 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       };
       // O_q += P_q . V(stage) : 8 k-steps of 16 kv rows; V is MN-major (hd contiguous), the two
       // 64-wide hd halves are 16 KB apart (LBO), 8-row kv groups 1 KB apart (SBO).
-      auto issue_pv = [&](int qt, int st, bool first) {
+      auto issue_pv = [&](int qt, int st, int half, bool first) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = half * 4 + kk;
           const uint64_t db = make_smem_desc_sw128(v_addr + st * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
           umma_ts(tmem_base + 256 + qt * 128, tmem_base + qt * 128 + 8 * k, db, idesc_pv,
                   (first && k == 0) ? 0u : 1u);
         }
       };
 
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (lane == 0) {
-        issue_qk(0, 0);
-        tc_commit(&s_full[0]);
-        issue_qk(1, 0);
-        tc_commit(&s_full[1]);
-        tc_commit(&k_empty[0]);
-      }
-      __syncwarp();
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int stn = (j + 1) & 1;
-        const uint32_t phn = ((j + 1) >> 1) & 1;
-        mbar_wait(&v_full[st], ph);
-        for (int qt = 0; qt < 2; ++qt) {
-          mbar_wait(&p_full[qt], j & 1);
-          if (qt == 0 && j + 1 < n_tiles) mbar_wait(&k_full[stn], phn);
-          tc_fence_after();
-          if (lane == 0) {
-            issue_pv(qt, st, j == 0);
-            if (qt == 1) tc_commit(&v_empty[st]);
-            if (j + 1 < n_tiles) {
-              issue_qk(qt, stn);
-              tc_commit(&s_full[qt]);
-              if (qt == 1) tc_commit(&k_empty[stn]);
-            }
-          }
-          __syncwarp();
+      int g = 0, piece = 0;
+      for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
+        const int n = piece_info(p, pi).n;
+        mbar_wait(q_full, piece & 1);
+        mbar_wait(&k_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_qk(0, g & 1);
+          tc_commit(&s_full[0]);
+          issue_qk(1, g & 1);
+          tc_commit(&s_full[1]);
+          tc_commit(&k_empty[g & 1]);
+          if (n == 1) tc_commit(q_empty);
         }
+        __syncwarp();
+        for (int jj = 0; jj < n; ++jj) {
+          const int gj = g + jj;
+          const int st = gj & 1;
+          const uint32_t ph = (gj >> 1) & 1;
+          const int stn = (gj + 1) & 1;
+          const uint32_t phn = ((gj + 1) >> 1) & 1;
+          mbar_wait(&v_full[st], ph);
+          for (int qt = 0; qt < 2; ++qt) {
+            // P arrives in two halves (KV rows 0-63, 64-127) so that P.V starts while the second half is still
+            // being exponentiated
+#if MMPL_ATTN_HALVES
+            mbar_wait(&p_full[2 * qt], gj & 1);
+            if (jj == 0) mbar_wait(&o_empty[qt], (piece & 1) ^ 1);  // previous piece's O has been read out
+            tc_fence_after();
+            if (lane == 0) issue_pv(qt, st, 0, jj == 0);
+            __syncwarp();
+            mbar_wait(&p_full[2 * qt + 1], gj & 1);
+#else
+            mbar_wait(&p_full[2 * qt + 1], gj & 1);
+            if (jj == 0) mbar_wait(&o_empty[qt], (piece & 1) ^ 1);
+            tc_fence_after();
+            if (lane == 0) issue_pv(qt, st, 0, jj == 0);
+            __syncwarp();
+#endif
+            if (qt == 0 && jj + 1 < n) mbar_wait(&k_full[stn], phn);
+            tc_fence_after();
+            if (lane == 0) {
+              issue_pv(qt, st, 1, false);
+              if (qt == 1) tc_commit(&v_empty[st]);
+              if (jj + 1 < n) {
+                issue_qk(qt, stn);
+                tc_commit(&s_full[qt]);
+                if (qt == 1) {
+                  tc_commit(&k_empty[stn]);
+                  if (jj + 2 == n) tc_commit(q_empty);  // last QK of the piece issued: Q smem may be reloaded
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (lane == 0) tc_commit(o_full);
+        __syncwarp();
+        g += n;
       }
-      if (lane == 0) tc_commit(o_full);
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------- softmax
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(224));
-    const int qt = (warp - 4) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MMPL_ATTN_SOFTMAX_REGS));
+    const int qt = (warp - kFirstSoftmaxWarp) >> 2;
     const int lane_base = (warp & 3) * 32;
     const uint32_t t_lane = static_cast<uint32_t>(lane_base) << 16;
     const uint32_t t_s = tmem_base + t_lane + qt * 128;
     const uint32_t t_o = tmem_base + t_lane + 256 + qt * 128;
-    const int q_row = q_row0 + qt * kQTile + lane_base + lane;
-    float m_run = -INFINITY;  // running max, in the scaled log2 domain
-    float l_run = 0.f;
-    int j = 0;
-    for (int sg = 0; sg < p.nseg; ++sg) {
-      const int nt = (p.seg_rows[sg] + kKVTile - 1) / kKVTile;
-      for (int t = 0; t < nt; ++t, ++j) {
-        const int valid = min(kKVTile, p.seg_rows[sg] - t * kKVTile);
-        mbar_wait(&s_full[qt], j & 1);
+    const int row_in_unit = qt * kQTile + lane_base + lane;
+    int g = 0, piece = 0;
+    for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
+      const Piece pc = piece_info(p, pi);
+      const int u = pc.u, t0 = pc.t0, n = pc.n, head = pc.head;
+      const int q_row = pc.q_row0 + row_in_unit;
+      float m_run = -INFINITY;  // running max, in the scaled log2 domain
+      float l_run = 0.f;
+      TileIter it;
+      it.init(p, t0);
+      for (int jj = 0; jj < n; ++jj, it.next(p)) {
+        const int valid = it.valid();
+        mbar_wait(&s_full[qt], (g + jj) & 1);
         tc_fence_after();
-        uint32_t s[128];
+        uint32_t sv[128];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
         tmem_ld_wait();
         if (valid < kKVTile) {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
-            if (c >= valid) s[c] = 0xFF800000u;  // -inf
+            if (c >= valid) sv[c] = 0xFF800000u;  // -inf
         }
-        float mx = __uint_as_float(s[0]);
+        float mx = __uint_as_float(sv[0]);
 #pragma unroll
-        for (int c = 1; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+        for (int c = 1; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
         const bool grow = m_new > m_run + 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+          const float alpha = fast_exp2(m_run - m_new);
           l_run *= alpha;
           m_run = m_new;
-          if (j > 0) {
+          if (jj > 0) {
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
               uint32_t o[32];
@@ -245,40 +372,67 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         uint32_t pk[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -m_run));
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, -m_run));
           sum += p0 + p1;
           pk[c] = pack_bf16x2(p0, p1);
         }
-        l_run += sum;
         tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+#if MMPL_ATTN_HALVES
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * qt]);
+#endif
         tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[qt]);
+        if (lane == 0) mbar_arrive(&p_full[2 * qt + 1]);
+        l_run += sum;
       }
-    }
-    // epilogue: O / l -> bf16 -> out[q_row, head*128 : head*128+128]
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    __nv_bfloat16* orow = p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD;
+      // piece epilogue
+      mbar_wait(o_full, piece & 1);
+      tc_fence_after();
+      if (p.split == 1) {
+        // whole unit: O / l -> bf16 -> out[q_row, head*128 : head*128+128]
+        const float inv_l = 1.0f / l_run;
+        __nv_bfloat16* orow = p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32(t_o + c * 32, o);
-      tmem_ld_wait();
-      if (q_row < p.Lq) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_o + c * 32, o);
+          tmem_ld_wait();
+          if (q_row < p.Lq) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
+            for (int gq = 0; gq < 4; ++gq) {
+              uint32_t w[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            w[i] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * i]) * inv_l, __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              for (int i = 0; i < 4; ++i)
+                w[i] = pack_bf16x2(__uint_as_float(o[gq * 8 + 2 * i]) * inv_l, __uint_as_float(o[gq * 8 + 2 * i + 1]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
         }
+      } else {
+        // partial unit: un-normalised fp32 O and (m, l) to the workspace slot of this piece
+        const int64_t base = (static_cast<int64_t>(u) * p.split + pc.chunk) * kUnitRows + row_in_unit;
+        float* po = p.part_o + base * kHD;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_o + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq)
+            *reinterpret_cast<uint4*>(po + c * 32 + gq * 4) = make_uint4(o[gq * 4], o[gq * 4 + 1], o[gq * 4 + 2], o[gq * 4 + 3]);
+        }
+        *reinterpret_cast<float2*>(p.part_ml + base * 2) = make_float2(m_run, l_run);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[qt]);
+      g += n;
     }
   }
 
@@ -290,21 +444,55 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 }
 
-int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
+// Merges the pieces of every unit that was split across CTAs:
+//   out = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i,  M = max_i m_i.   One warp per query row.
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const AttnParams p) {
+  const int u = blockIdx.x >> 5;
+  const int row_in_unit = (blockIdx.x & 31) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int np = p.split;
+  const int head = u / p.QP;
+  const int q_row = (u - head * p.QP) * kUnitRows + row_in_unit;
+  if (q_row >= p.Lq) return;
+  const int64_t base = static_cast<int64_t>(u) * p.split * kUnitRows + row_in_unit;
+  float M = -INFINITY;
+  for (int i = 0; i < np; ++i) M = fmaxf(M, p.part_ml[(base + static_cast<int64_t>(i) * kUnitRows) * 2]);
+  float L = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < np; ++i) {
+    const int64_t r = base + static_cast<int64_t>(i) * kUnitRows;
+    const float2 ml = *reinterpret_cast<const float2*>(p.part_ml + r * 2);
+    const float w = exp2f(ml.x - M);
+    L += w * ml.y;
+    const float4 o = *reinterpret_cast<const float4*>(p.part_o + r * kHD + lane * 4);
+    acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+  }
+  const float inv = 1.0f / L;
+  uint2 w2 = make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
+  *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD + lane * 4) = w2;
+}
+
+// Workspace for partial pieces (grown on demand; one per process, used by launches on one stream at a time).
+static float* g_part = nullptr;
+static size_t g_part_bytes = 0;
+int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
                     int64_t ldkv0, int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1,
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
-                    int64_t ldo, float softmax_scale, cudaStream_t stream) {
+                    int64_t ldo, float softmax_scale, int force_split, cudaStream_t stream) {
   MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "flash_attn: requires an sm_100 device");
   MMPL_CHECK(Lq > 0 && H > 0, MMPL_ERR_SHAPE, "flash_attn: bad Lq=%d H=%d", Lq, H);
   MMPL_CHECK(nseg >= 1 && nseg <= kMaxSeg, MMPL_ERR_SHAPE, "flash_attn: nseg=%d out of [1,%d]", nseg, kMaxSeg);
   MMPL_CHECK(ldo % 8 == 0, MMPL_ERR_SHAPE, "flash_attn: ldo must be a multiple of 8");
   AttnParams p{};
   p.Lq = Lq;
+  p.H = H;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.nseg = nseg;
   bool uses1 = false;
+  int T = 0;
   for (int i = 0; i < nseg; ++i) {
     const int src = seg_src ? seg_src[i] : 0;
     const int lim = src ? rows1 : rows0;
@@ -314,6 +502,7 @@ int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
     p.seg_rows[i] = seg_rows[i];
     p.seg_src[i] = src;
     uses1 |= (src != 0);
+    T += (seg_rows[i] + kKVTile - 1) / kKVTile;
   }
   MMPL_CHECK(!uses1 || (k1 && v1), MMPL_ERR_ARG, "flash_attn: segment refers to a missing second K/V source");
   const CUtensorMap* mq = get_tensor_map_bf16(q, Lq, static_cast<uint64_t>(H) * kHD, ldq, 128);
@@ -323,15 +512,56 @@ int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   const CUtensorMap* mv1 = uses1 ? get_tensor_map_bf16(v1, rows1, static_cast<uint64_t>(H) * kHD, ldkv1, 128) : mv0;
   if (!mq || !mk0 || !mv0 || !mk1 || !mv1) return MMPL_ERR_CUDA;
 
+  // work partition: U units of T tiles, each cut into `split` KV chunks, over G persistent CTAs.
+  // Cost model (in KV-tile times per SM): rounds * (tiles per piece + fixed cost per piece) + merge traffic.
+  p.QP = (Lq + kUnitRows - 1) / kUnitRows;
+  p.T = T;
+  const int U = p.QP * H;
+  const int sms = sm_count();
+  int best_split = 1;
+  {
+    // measured on B200 (tools/bench_kernels.py): a piece costs ~6 tile times on top of its tiles (Q load, pipeline
+    // fill, epilogue); merging costs 2 x 128 KB of HBM traffic per (unit, chunk) ~ 0.029 tile times each.
+    const double piece_fixed = 6.0;
+    double best = 1e30;
+    for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
+      if (sp > 1 && T / sp < 8) break;
+      const int rounds = (U * sp + sms - 1) / sms;
+      const double cost = rounds * (static_cast<double>(T) / sp + piece_fixed) + (sp > 1 ? 0.0291 * U * sp : 0.0);
+      if (cost < best - 1e-9) { best = cost; best_split = sp; }
+    }
+  }
+  if (force_split > 0 && force_split <= T) best_split = force_split;
+  p.split = best_split;
+  p.n_pieces = U * p.split;
+  static const bool nonpersistent = getenv("MMPL_ATTN_NONPERSISTENT") != nullptr;
+  const int G = (p.n_pieces < sms || nonpersistent) ? p.n_pieces : sms;
+  if (p.split > 1) {
+    const size_t need = static_cast<size_t>(U) * p.split * kUnitRows * (kHD + 2) * sizeof(float);
+    if (need > g_part_bytes) {
+      if (g_part) MMPL_CUDA(cudaFree(g_part));
+      g_part = nullptr;
+      g_part_bytes = 0;
+      MMPL_CUDA(cudaMalloc(&g_part, need));
+      g_part_bytes = need;
+    }
+    p.part_o = g_part;
+    p.part_ml = g_part + static_cast<size_t>(U) * p.split * kUnitRows * kHD;
+  }
+
   static bool attr_set = false;
   if (!attr_set) {
     MMPL_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
-  dim3 grid((Lq + 2 * kQTile - 1) / (2 * kQTile), H);
-  flash_attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(*mq, *mk0, *mv0, *mk1, *mv1, p);
+  flash_attn_kernel<<<G, kAttnThreads, kAttnSmem, stream>>>(*mq, *mk0, *mv0, *mk1, *mv1, p);
   MMPL_CUDA(cudaGetLastError());
+  if (p.split > 1) {
+    attn_combine_kernel<<<U * 32, 256, 0, stream>>>(p);
+    MMPL_CUDA(cudaGetLastError());
+  }
   return MMPL_OK;
 }
 
+}  // namespace MMPL_ATTN_NS
 }  // namespace mmpl

@@ -56,6 +56,63 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// Epilogue of one accumulator row: `taddr` addresses this warp's 32 TMEM lanes at the tile's first column; the
+// thread owns output row `row`, columns [col_base, col_base + BN). Rounds to bf16 where the reference does.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int col_base) {
+  const bool row_ok = row < p.M;
+  const __nv_bfloat16* gate_row = nullptr;
+  if (EPI == MMPL_EPI_BIAS_GATE_RES && row_ok)
+    gate_row = p.gate + static_cast<int64_t>(row / p.rows_per_frame) * p.gate_stride;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr + c * 32, acc);
+    tmem_ld_wait();
+    const int col0 = col_base + c * 32;
+    if (row_ok && col0 < p.N) {
+      // N is a multiple of 8; handle the chunk in 8-column (16-byte) groups.
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        if (col >= p.N) break;
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+        uint4 rv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
+        if (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES)
+          rv = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(row) * p.ldr + col);
+        if (EPI == MMPL_EPI_BIAS_GATE_RES)
+          gv = __ldg(reinterpret_cast<const uint4*>(gate_row + col));
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+          float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+          if (EPI == MMPL_EPI_BIAS_GELU) {
+            y0 = gelu_tanh_f(y0);
+            y1 = gelu_tanh_f(y1);
+          } else if (EPI == MMPL_EPI_BIAS_SILU) {
+            y0 = silu_f(y0);
+            y1 = silu_f(y1);
+          } else if (EPI == MMPL_EPI_BIAS_RES) {
+            y0 = bf16_lo(rw[j]) + y0;
+            y1 = bf16_hi(rw[j]) + y1;
+          } else if (EPI == MMPL_EPI_BIAS_GATE_RES) {
+            y0 = bf16_lo(rw[j]) + bf16_round(y0 * bf16_lo(gw[j]));
+            y1 = bf16_hi(rw[j]) + bf16_round(y1 * bf16_hi(gw[j]));
+          }
+          ow[j] = pack_bf16x2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row) * p.ldo + col) =
+            make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -162,57 +219,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const int row = m_blk * kBM + lane_base + lane;
-      const bool row_ok = row < p.M;
-      const __nv_bfloat16* gate_row = nullptr;
-      if (EPI == MMPL_EPI_BIAS_GATE_RES && row_ok)
-        gate_row = p.gate + static_cast<int64_t>(row / p.rows_per_frame) * p.gate_stride;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN + c * 32, acc);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.N) {
-          // N is a multiple of 8; handle the chunk in 8-column (16-byte) groups.
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= p.N) break;
-            uint4 bv = make_uint4(0, 0, 0, 0);
-            if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-            uint4 rv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
-            if (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES)
-              rv = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(row) * p.ldr + col);
-            if (EPI == MMPL_EPI_BIAS_GATE_RES)
-              gv = __ldg(reinterpret_cast<const uint4*>(gate_row + col));
-            const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
-            const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
-            uint32_t ow[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
-              float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
-              if (EPI == MMPL_EPI_BIAS_GELU) {
-                y0 = gelu_tanh_f(y0);
-                y1 = gelu_tanh_f(y1);
-              } else if (EPI == MMPL_EPI_BIAS_SILU) {
-                y0 = silu_f(y0);
-                y1 = silu_f(y1);
-              } else if (EPI == MMPL_EPI_BIAS_RES) {
-                y0 = bf16_lo(rw[j]) + y0;
-                y1 = bf16_hi(rw[j]) + y1;
-              } else if (EPI == MMPL_EPI_BIAS_GATE_RES) {
-                y0 = bf16_lo(rw[j]) + bf16_round(y0 * bf16_lo(gw[j]));
-                y1 = bf16_hi(rw[j]) + bf16_round(y1 * bf16_hi(gw[j]));
-              }
-              ow[j] = pack_bf16x2(y0, y1);
-            }
-            *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row) * p.ldo + col) =
-                make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -224,6 +231,177 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a pair of CTAs (one cluster of 2, same TPC) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2 (M = 256, N = 256). Each CTA loads 128 rows of A and 128 rows (= N/2) of W
+// per 64-wide k block (32 KB per stage instead of 48 KB) and holds 128 accumulator rows x 256 columns in
+// its own TMEM, double-buffered. Per-SM L2->SMEM traffic drops from 96 to 64 B/clk at full MMA rate,
+// which is what bounds the single-CTA 128x256 kernel (ncu: tensor pipe ~48 % active).
+// Barriers: the leader's full[s] collects the TMA bytes of both CTAs (expect_tx = 64 KB); the leader's
+// MMA thread releases smem slots and publishes accumulators with multicast commits to both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's tmem_empty.
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = 2 * kBM * kBK * 2;  // 16 KB A + 16 KB W per CTA
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+constexpr int kPairBN = 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const GemmParams p) {
+  constexpr int ST = kPairStages;
+  constexpr int BN = kPairBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + ST * (kPairStageBytes / 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * kPairStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + ST;
+  uint64_t* tmem_full = bars + 2 * ST;
+  uint64_t* tmem_empty = bars + 2 * ST + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int num_tiles = p.tiles_m * p.tiles_n;  // tiles of 256 x 256
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < ST; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs, own halves)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m_blk = t % p.tiles_m;
+        const int n_blk = t / p.tiles_m;
+        const int row_a = m_blk * 256 + static_cast<int>(cta) * kBM;
+        const int row_b = n_blk * BN + static_cast<int>(cta) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kPairStageBytes);
+          tma_load_2d_2cta(smem_a + s * (kPairStageBytes / 2), &map_a, &full_bar[s], kb * kBK, row_a, kEvictNormal);
+          tma_load_2d_2cta(smem_b + s * (kPairStageBytes / 2), &map_b, &full_bar[s], kb * kBK, row_b, kEvictLast);
+          if (++s == ST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * (kPairStageBytes / 2)), 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * (kPairStageBytes / 2)), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_2cta(&empty_bar[s], 0x3);
+            if (kb == num_kb - 1) tc_commit_2cta(&tmem_full[as], 0x3);
+          }
+          __syncwarp();
+          if (++s == ST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int lane_base = (warp & 3) * 32;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int m_blk = t % p.tiles_m;
+      const int n_blk = t / p.tiles_m;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      const int row = m_blk * 256 + static_cast<int>(cta) * kBM + lane_base + lane;
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+template <int EPI>
+static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
+  auto kern = gemm_bf16_pair_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + 255) / 256;
+  p.tiles_n = (p.N + kPairBN - 1) / kPairBN;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  kern<<<2 * pairs, kGemmThreads, kPairSmemBytes, stream>>>(*ma, *mb, p);
+  MMPL_CUDA(cudaGetLastError());
+  return MMPL_OK;
+}
+
+static int dispatch_epi_pair(int epi, const CUtensorMap* ma, const CUtensorMap* mb, const GemmParams& p,
+                             cudaStream_t stream) {
+  switch (epi) {
+    case MMPL_EPI_BIAS: return launch_gemm_pair<MMPL_EPI_BIAS>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GELU: return launch_gemm_pair<MMPL_EPI_BIAS_GELU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_SILU: return launch_gemm_pair<MMPL_EPI_BIAS_SILU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_RES: return launch_gemm_pair<MMPL_EPI_BIAS_RES>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GATE_RES: return launch_gemm_pair<MMPL_EPI_BIAS_GATE_RES>(ma, mb, p, stream);
+    default: set_error("gemm: unknown epilogue %d", epi); return MMPL_ERR_ARG;
   }
 }
 
@@ -287,6 +465,25 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   if (epilogue == MMPL_EPI_BIAS_GATE_RES)
     MMPL_CHECK(gate != nullptr && rows_per_frame > 0 && gate_stride % 8 == 0, MMPL_ERR_ARG,
                "gemm: gate epilogue needs gate, rows_per_frame > 0 and gate_stride %% 8 == 0");
+  // tile_n 512 selects the cta_group::2 kernel (256 x 256 tile per CTA pair); auto-selected for large problems
+  const bool use_pair = force_bn == 512 || (force_bn == 0 && N % 256 == 0 && M >= 512);
+  if (use_pair) {
+    MMPL_CHECK(N % 8 == 0, MMPL_ERR_SHAPE, "gemm: N must be a multiple of 8");
+    const CUtensorMap* pa = get_tensor_map_bf16(a, M, K, lda, kBM);
+    const CUtensorMap* pb = get_tensor_map_bf16(w, N, K, ldw, kBM);
+    if (!pa || !pb) return MMPL_ERR_CUDA;
+    GemmParams pp{};
+    pp.M = M; pp.N = N; pp.K = K;
+    pp.out = static_cast<__nv_bfloat16*>(out);
+    pp.ldo = ldo;
+    pp.bias = static_cast<const __nv_bfloat16*>(bias);
+    pp.res = static_cast<const __nv_bfloat16*>(residual);
+    pp.ldr = ldr;
+    pp.gate = static_cast<const __nv_bfloat16*>(gate);
+    pp.gate_stride = gate_stride;
+    pp.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
+    return dispatch_epi_pair(epilogue, pa, pb, pp, stream);
+  }
   const int bn = force_bn ? force_bn : pick_bn(M, N);
   MMPL_CHECK(bn == 64 || bn == 128 || bn == 256, MMPL_ERR_ARG, "gemm: tile width %d not supported", bn);
 

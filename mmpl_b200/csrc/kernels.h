@@ -14,6 +14,8 @@ int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
                     int64_t ldo, float softmax_scale, cudaStream_t stream);
 
+void flash_attn_force_split(int split);
+
 int ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                 const void* scale, int64_t mod_stride, int rows_per_frame, cudaStream_t st);
 int ln_affine(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* weight,

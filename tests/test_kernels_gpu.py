@@ -1,6 +1,7 @@
 """Per-kernel parity on the GPU: every C-ABI kernel entry point against the oracle primitive it replaces
 (oracle/causal_wan_oracle.py, evaluated with torch ops on the same device for speed)."""
 import math
+import types
 
 import pytest
 import torch
@@ -41,6 +42,9 @@ def _report(name, got, ref, atol, rtol, outlier_frac=0.0, outlier_abs=0.0):
     (300, 256, 128, 0), (300, 256, 192, 64), (300, 256, 192, 128), (300, 512, 192, 256),
     (1170, 1536, 1536, 0), (4680, 1536, 1536, 0), (4680, 4608, 1536, 0), (4680, 8960, 1536, 0), (4680, 1536, 8960, 0),
     (4680, 64, 1536, 0), (4680, 1536, 64, 0), (512, 1536, 4096, 0),
+    # tile 512 = the cta_group::2 kernel (256 x 256 per CTA pair); 256 = force the single-CTA kernel
+    (256, 256, 64, 512), (300, 512, 192, 512), (4680, 1536, 1536, 512), (4680, 4608, 1536, 512), (4680, 8960, 1536, 512),
+    (4680, 1536, 8960, 512), (10920, 5120, 5120, 512), (4680, 1536, 1536, 256), (4680, 1536, 1536, 128),
 ])
 def test_gemm_bias(M, N, K, tile):
     ops = _ops()
@@ -49,9 +53,12 @@ def test_gemm_bias(M, N, K, tile):
     _report(f"gemm {M}x{N}x{K} tile={tile}", got, O.linear(x, w, b), atol=2e-2, rtol=2e-2)
 
 
-@pytest.mark.parametrize("M,N,K", [(1170, 1536, 1536), (4680, 1536, 1536)])
-def test_gemm_epilogues(M, N, K):
+@pytest.mark.parametrize("M,N,K,tile", [(1170, 1536, 1536, 0), (4680, 1536, 1536, 0), (4680, 1536, 1536, 128), (1170, 1536, 1536, 512)])
+def test_gemm_epilogues(M, N, K, tile):
+    import functools
     ops = _ops()
+    ops = types.SimpleNamespace(**{k: getattr(ops, k) for k in dir(ops) if not k.startswith("__")})
+    ops.linear = functools.partial(ops.linear, tile_n=tile)
     frames, fs = 3, M // 3
     x, w, b = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, scale=0.1, seed=3)
     res, gate = _rand(M, N, seed=4), _rand(frames, 6, N, seed=5)
@@ -93,6 +100,22 @@ def test_flash_attn_strided_window_and_segments():
     got = ops.flash_attn(q, cache_k, cache_v, segments=[(0, 390), (0, 260, 1)], k_tail=tk, v_tail=tv)
     ref = O.attention(q, torch.cat([cache_k[:390], tk]), torch.cat([cache_v[:390], tv]))
     _report("tail", got, ref, 1e-2, 2e-2)
+
+
+@pytest.mark.parametrize("split", [1, 2, 3, 5])
+def test_flash_attn_forced_kv_split(split):
+    """Every unit cut into `split` KV chunks and merged by the combine kernel must equal the unsplit result."""
+    from mmpl_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    q, k, v = _rand(700, 3, 128, seed=1), _rand(5000, 3, 128, seed=2), _rand(5000, 3, 128, seed=3)
+    try:
+        lib.mmpl_attn_set_split(split)
+        got = ops.flash_attn(q, k, v, segments=[(0, 1300), (2000, 2900)])
+    finally:
+        lib.mmpl_attn_set_split(0)
+    idx = torch.cat([torch.arange(0, 1300), torch.arange(2000, 4900)]).to(DEV)
+    _report(f"attn split={split}", got, O.attention(q, k[idx], v[idx]), atol=1e-2, rtol=2e-2)
 
 
 def test_flash_attn_large_logits():
