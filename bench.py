@@ -35,6 +35,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "denoised_latent_frames_per_s"
 UNIT = "latent frames/s"
@@ -257,6 +260,10 @@ def run_ours(args):
     ms_total = timed(step_resident, K)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.mmpl_total_launches(0))
+    if world > 1:
+        lt = torch.tensor([launches], device=device, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     _lib.check(lib.mmpl_profile_read(ctx, ms_arr, work_arr, n_arr, 1))
     attn_ms, attn_flops, attn_n = ms_arr[0], work_arr[0], n_arr[0]
     _lib.check(lib.mmpl_profile_enable(ctx, 0))

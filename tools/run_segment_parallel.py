@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""MMPL segment-parallel long-video generation (BASELINE.json configs 3-5) with synthetic weights and inputs.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \\
+      tools/run_segment_parallel.py --model 14B --segments 4 --sampling-steps 50
+
+One process per GPU; segment k runs on rank k % G; anchors go rank -> rank over NCCL (mmpl_b200.segment_parallel).
+Prints one JSON line with denoised latent frames/s per box = segments * 21 / wall time of the whole chain (device
+time, max over ranks), the per-segment times and the anchor bytes moved. `--sampling-steps` below the reference's 50
+shortens every stage proportionally (same schedule, same kernels, fewer UniPC steps) for quick scaling checks.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmpl_b200.causal_model import CausalFPSWanModel  # noqa: E402
+from mmpl_b200.pipeline import CausalFPSInferencePipeline  # noqa: E402
+from mmpl_b200.segment_parallel import (AnchorChannel, I2V_ANCHOR_SHAPE, SegmentParallelRunner,  # noqa: E402
+                                        T2V_ANCHOR_SHAPE)
+from mmpl_b200.wan_wrapper import MODEL_CONFIGS, WanFPSWrapper  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="14B", choices=["14B", "1.3B"])
+    ap.add_argument("--segments", type=int, default=4)
+    ap.add_argument("--sampling-steps", type=int, default=50)
+    ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
+    ap.add_argument("--i2v", action="store_true")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    dims = dict(MODEL_CONFIGS["Wan2.1-T2V-14B" if a.model == "14B" else "Wan2.1-T2V-1.3B"])
+    if a.layers:
+        dims["num_layers"] = a.layers
+    torch.manual_seed(0)  # identical random-init replica on every rank
+    t0 = time.perf_counter()
+    with torch.device(dev):
+        model = CausalFPSWanModel(**dims)
+    model = model.to(torch.bfloat16).eval().requires_grad_(False)
+    gen = WanFPSWrapper(model=model, timestep_shift=5.0)
+    build_s = time.perf_counter() - t0
+    prompt = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).to(dev)
+    negative = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(dev)
+
+    class Text(torch.nn.Module):
+        def forward(self, text_prompts):
+            return {"prompt_embeds": negative if text_prompts[0] == "__negative__" else prompt}
+
+    class VAE(torch.nn.Module):
+        def decode_to_pixel(self, latents, use_cache=False):
+            return latents
+
+    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="__negative__",
+                                 independent_first_frame=False, sampling_steps=a.sampling_steps, model_kwargs={}, i2v=a.i2v)
+    pipe = CausalFPSInferencePipeline(args, dev, generator=gen, text_encoder=Text(), vae=VAE(), device_cond=dev, device_uncond=dev)
+    channel = AnchorChannel()
+    if world > 1:  # create the NCCL point-to-point connections outside the timed region
+        buf = torch.zeros(8, device=dev)
+        nxt, prv = (rank + 1) % world, (rank - 1) % world
+        ops = [dist.P2POp(dist.isend, buf, nxt), dist.P2POp(dist.irecv, torch.empty_like(buf), prv)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    runner = SegmentParallelRunner(pipe, channel, anchor_shape=I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE)
+
+    def make_noise(seg):
+        g = torch.Generator().manual_seed(100 + seg)
+        return torch.randn(1, 21, 16, 60, 104, generator=g).to(torch.bfloat16).to(dev)
+
+    if a.i2v:  # the i2v schedule needs a first frame for segment 0 (VAE-encoded image in the reference)
+        first = torch.randn(1, 1, 16, 60, 104, generator=torch.Generator().manual_seed(7)).to(torch.bfloat16).to(dev)
+        orig_connect = runner.connect
+        runner.connect = lambda anchors: orig_connect(anchors)
+        inference = pipe.inference
+        pipe.inference = lambda noise, text_prompts, initial_latent=None, return_latents=True: inference(
+            noise=noise, text_prompts=text_prompts, initial_latent=first if initial_latent is None else initial_latent,
+            return_latents=return_latents)
+
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    model.launch_count(reset=True)
+    outs = runner.run(make_noise, ["synthetic prompt"], a.segments)
+    e1.record()
+    torch.cuda.synchronize()
+    my_ms = e0.elapsed_time(e1)
+    wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    total_wall = time.perf_counter() - wall0
+    ms = torch.tensor([my_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    finite = all(torch.isfinite(v.float()).all().item() for v in outs.values())
+    info = dict(rank=rank, segments=sorted(outs), ms=my_ms, launches=model.launch_count(), finite=finite,
+                anchor_bytes_sent=channel.bytes_sent, log=runner.log)
+    gathered = [info]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, info)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
+            "value": a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
+            "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.segments} segments x 21 latent frames 60x104, "
+                                   f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
+                       "parallelism": f"segment-parallel x{world}, anchors over NCCL send/recv"},
+            "model_build_s": build_s, "ranks": gathered}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
