@@ -398,6 +398,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // whole unit: O / l -> bf16 -> out[q_row, head*128 : head*128+128]
         const float inv_l = 1.0f / l_run;
         __nv_bfloat16* orow = p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD;
+        const bool wide_out = (p.ldo % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t o[32];
@@ -405,12 +406,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           tmem_ld_wait();
           if (q_row < p.Lq) {
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              uint32_t w[4];
+            for (int gq = 0; gq < 2; ++gq) {
+              uint32_t w[8];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(__uint_as_float(o[gq * 8 + 2 * i]) * inv_l, __uint_as_float(o[gq * 8 + 2 * i + 1]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + gq * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf16x2(__uint_as_float(o[gq * 16 + 2 * i]) * inv_l, __uint_as_float(o[gq * 16 + 2 * i + 1]) * inv_l);
+              if (wide_out) {
+                st_global_v8(orow + c * 32 + gq * 16, w);
+              } else {
+                *reinterpret_cast<uint4*>(orow + c * 32 + gq * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(orow + c * 32 + gq * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              }
             }
           }
         }
@@ -424,8 +430,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           tmem_ld_32x32(t_o + c * 32, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int gq = 0; gq < 8; ++gq)
-            *reinterpret_cast<uint4*>(po + c * 32 + gq * 4) = make_uint4(o[gq * 4], o[gq * 4 + 1], o[gq * 4 + 2], o[gq * 4 + 3]);
+          for (int gq = 0; gq < 4; ++gq) {
+            const uint32_t w[8] = {o[gq * 8], o[gq * 8 + 1], o[gq * 8 + 2], o[gq * 8 + 3],
+                                   o[gq * 8 + 4], o[gq * 8 + 5], o[gq * 8 + 6], o[gq * 8 + 7]};
+            st_global_v8(po + c * 32 + gq * 8, w);  // workspace rows are 512 B, cudaMalloc-aligned
+          }
         }
         *reinterpret_cast<float2*>(p.part_ml + base * 2) = make_float2(m_run, l_run);
       }

@@ -71,43 +71,77 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     tmem_ld_wait();
     const int col0 = col_base + c * 32;
     if (row_ok && col0 < p.N) {
-      // N is a multiple of 8; handle the chunk in 8-column (16-byte) groups.
+      // N is a multiple of 8: 8-column (16-byte) groups; two groups are stored together as one 32-byte sector
+      // (st.global.v8) when the row pitch allows, so no sector is written partially.
+      const bool wide = (p.ldo % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = col0 + g * 8;
-        if (col >= p.N) break;
-        uint4 bv = make_uint4(0, 0, 0, 0);
-        if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-        uint4 rv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
-        if (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES)
-          rv = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(row) * p.ldr + col);
-        if (EPI == MMPL_EPI_BIAS_GATE_RES)
-          gv = __ldg(reinterpret_cast<const uint4*>(gate_row + col));
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
-        const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
-        uint32_t ow[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
-          float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
-          if (EPI == MMPL_EPI_BIAS_GELU) {
-            y0 = gelu_tanh_f(y0);
-            y1 = gelu_tanh_f(y1);
-          } else if (EPI == MMPL_EPI_BIAS_SILU) {
-            y0 = silu_f(y0);
-            y1 = silu_f(y1);
-          } else if (EPI == MMPL_EPI_BIAS_RES) {
-            y0 = bf16_lo(rw[j]) + y0;
-            y1 = bf16_hi(rw[j]) + y1;
-          } else if (EPI == MMPL_EPI_BIAS_GATE_RES) {
-            y0 = bf16_lo(rw[j]) + bf16_round(y0 * bf16_lo(gw[j]));
-            y1 = bf16_hi(rw[j]) + bf16_round(y1 * bf16_hi(gw[j]));
+      for (int g2 = 0; g2 < 2; ++g2) {
+        uint32_t ow[8];
+        bool have[2] = {false, false};
+        // residual: one 32-byte load per 16 columns when the layout allows it
+        uint32_t rres[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES) {
+          const __nv_bfloat16* src = p.res + static_cast<int64_t>(row) * p.ldr + col0 + g2 * 16;
+          if (col0 + g2 * 16 + 16 <= p.N && (p.ldr % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 31) == 0)) {
+            asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(rres[0]), "=r"(rres[1]), "=r"(rres[2]), "=r"(rres[3]), "=r"(rres[4]), "=r"(rres[5]),
+                           "=r"(rres[6]), "=r"(rres[7])
+                         : "l"(src)
+                         : "memory");
+          } else {
+            if (col0 + g2 * 16 < p.N) {
+              const uint4 t = *reinterpret_cast<const uint4*>(src);
+              rres[0] = t.x; rres[1] = t.y; rres[2] = t.z; rres[3] = t.w;
+            }
+            if (col0 + g2 * 16 + 8 < p.N) {
+              const uint4 t = *reinterpret_cast<const uint4*>(src + 8);
+              rres[4] = t.x; rres[5] = t.y; rres[6] = t.z; rres[7] = t.w;
+            }
           }
-          ow[j] = pack_bf16x2(y0, y1);
         }
-        *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row) * p.ldo + col) =
-            make_uint4(ow[0], ow[1], ow[2], ow[3]);
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const int g = g2 * 2 + gg;
+          const int col = col0 + g * 8;
+          if (col >= p.N) continue;
+          have[gg] = true;
+          uint4 bv = make_uint4(0, 0, 0, 0);
+          if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+          uint4 rv = make_uint4(rres[gg * 4], rres[gg * 4 + 1], rres[gg * 4 + 2], rres[gg * 4 + 3]), gv = make_uint4(0, 0, 0, 0);
+          if (EPI == MMPL_EPI_BIAS_GATE_RES)
+            gv = __ldg(reinterpret_cast<const uint4*>(gate_row + col));
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+          const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
+            float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+            if (EPI == MMPL_EPI_BIAS_GELU) {
+              y0 = gelu_tanh_f(y0);
+              y1 = gelu_tanh_f(y1);
+            } else if (EPI == MMPL_EPI_BIAS_SILU) {
+              y0 = silu_f(y0);
+              y1 = silu_f(y1);
+            } else if (EPI == MMPL_EPI_BIAS_RES) {
+              y0 = bf16_lo(rw[j]) + y0;
+              y1 = bf16_hi(rw[j]) + y1;
+            } else if (EPI == MMPL_EPI_BIAS_GATE_RES) {
+              y0 = bf16_lo(rw[j]) + bf16_round(y0 * bf16_lo(gw[j]));
+              y1 = bf16_hi(rw[j]) + bf16_round(y1 * bf16_hi(gw[j]));
+            }
+            ow[gg * 4 + j] = pack_bf16x2(y0, y1);
+          }
+        }
+        __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0 + g2 * 16;
+        if (have[0] && have[1] && wide) {
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(ow[0]), "r"(ow[1]),
+                       "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                       : "memory");
+        } else {
+          if (have[0]) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          if (have[1]) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        }
       }
     }
   }
