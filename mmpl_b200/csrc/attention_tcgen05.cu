@@ -60,6 +60,11 @@ constexpr int kAttnSmem = 4 * kBoxBytes /*Q*/ + kKVStages * 2 * kBoxBytes /*K*/ 
                           kKVStages * 2 * kBoxBytes /*V*/ + 1024 + 256;
 constexpr int kMaxSeg = 8;
 constexpr int kUnitRows = 2 * kQTile;
+#ifndef MMPL_ATTN_POLY_NUM
+#define MMPL_ATTN_POLY_NUM 7
+#endif
+constexpr int kPolyNum = MMPL_ATTN_POLY_NUM;  // pairs per kPolyDen whose exp2 runs on the FMA/ALU pipes
+constexpr int kPolyDen = 16;
 
 struct AttnParams {
   int Lq, H;
@@ -368,14 +373,33 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
           }
         }
-        float sum = 0.f;
+        // P = 2^(S*scale - m): packed fp32x2 FMA for the scaling and the row sum; kPolyNum of every kPolyDen pairs
+        // are exponentiated on the FMA/ALU pipes (exp2_poly_x2) instead of the MUFU, which is otherwise the pipe
+        // that paces the softmax (16 ex2/clk/SM against 128 rows x 128 columns per tile).
+        uint64_t sum2 = pack_f32x2(0.f, 0.f);
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
         uint32_t pk[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, -m_run));
-          sum += p0 + p1;
+          const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sc2, nm2);
+          float p0, p1;
+          if ((c % kPolyDen) < kPolyNum) {
+            exp2_poly_x2(x2, p0, p1);
+          } else {
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+          }
+          sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
           pk[c] = pack_bf16x2(p0, p1);
+        }
+        float sum;
+        {
+          float s_lo, s_hi;
+          unpack_f32x2(sum2, s_lo, s_hi);
+          sum = s_lo + s_hi;
         }
         tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
 #if MMPL_ATTN_HALVES

@@ -50,6 +50,19 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
   uint4 v[NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) v[i] = xr[lane + 32 * i];
+  // the modulation / affine vectors are fetched together with the row, so their latency is paid once
+  const int frame = row / rows_per_frame;
+  const uint4* a_ptr = reinterpret_cast<const uint4*>(AFFINE ? scale : scale + static_cast<int64_t>(frame) * mod_stride);
+  const uint4* b_ptr = reinterpret_cast<const uint4*>(AFFINE ? shift : shift + static_cast<int64_t>(frame) * mod_stride);
+  constexpr bool kPrefetch = NCH <= 8;
+  uint4 av[kPrefetch ? NCH : 1], bv[kPrefetch ? NCH : 1];
+  if (kPrefetch) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      av[i] = __ldg(a_ptr + lane + 32 * i);
+      bv[i] = __ldg(b_ptr + lane + 32 * i);
+    }
+  }
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
@@ -71,16 +84,13 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
-  const int frame = row / rows_per_frame;
-  const uint4* a_ptr = reinterpret_cast<const uint4*>(AFFINE ? scale : scale + static_cast<int64_t>(frame) * mod_stride);
-  const uint4* b_ptr = reinterpret_cast<const uint4*>(AFFINE ? shift : shift + static_cast<int64_t>(frame) * mod_stride);
   uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     float f[8], a[8], b[8];
     unpack8(v[i], f);
-    unpack8(__ldg(a_ptr + lane + 32 * i), a);
-    unpack8(__ldg(b_ptr + lane + 32 * i), b);
+    unpack8(kPrefetch ? av[i] : __ldg(a_ptr + lane + 32 * i), a);
+    unpack8(kPrefetch ? bv[i] : __ldg(b_ptr + lane + 32 * i), b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float n = (f[j] - mean) * rstd;
@@ -194,23 +204,36 @@ qk_norm_rope_kv_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
   const int pt = p.frame_pos[fr];
   const int64_t dst_row = static_cast<int64_t>(p.kv_row[fr]) + rem;
 
-  uint4 v[NCH];
+  // all three rows are fetched up front (one memory latency instead of three); for the 14B width (NCH = 20) the
+  // registers do not allow it and q, k, v are processed one after the other
+  constexpr bool kTogether = NCH <= 8;
+  uint4 vq[NCH], vk[kTogether ? NCH : 1], vv[kTogether ? NCH : 1];
+  const uint4* rq = reinterpret_cast<const uint4*>(q_in + static_cast<int64_t>(row) * ld_in);
+  const uint4* rk = reinterpret_cast<const uint4*>(k_in + static_cast<int64_t>(row) * ld_in);
+  const uint4* rv = reinterpret_cast<const uint4*>(v_in + static_cast<int64_t>(row) * ld_in);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) vq[i] = rq[lane + 32 * i];
+  if (kTogether) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) vk[i] = rk[lane + 32 * i];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) vv[i] = rv[lane + 32 * i];
+  }
   // q
   {
-    const uint4* r = reinterpret_cast<const uint4*>(q_in + static_cast<int64_t>(row) * ld_in);
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) v[i] = r[lane + 32 * i];
-    rmsnorm_row<NCH>(v, wq, lane, p.eps);
-    rope_row<NCH>(v, rope_tab, lane, pt, ph, pw);
+    rmsnorm_row<NCH>(vq, wq, lane, p.eps);
+    rope_row<NCH>(vq, rope_tab, lane, pt, ph, pw);
     uint4* o = reinterpret_cast<uint4*>(q_out + static_cast<int64_t>(row) * ldq);
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = v[i];
+    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = vq[i];
   }
   // k
   {
-    const uint4* r = reinterpret_cast<const uint4*>(k_in + static_cast<int64_t>(row) * ld_in);
+    uint4 (&v)[NCH] = *reinterpret_cast<uint4(*)[NCH]>(kTogether ? &vk[0] : &vq[0]);
+    if (!kTogether) {
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) v[i] = r[lane + 32 * i];
+      for (int i = 0; i < NCH; ++i) v[i] = rk[lane + 32 * i];
+    }
     rmsnorm_row<NCH>(v, wk, lane, p.eps);
     rope_row<NCH>(v, rope_tab, lane, pt, ph, pw);
     uint4* o = reinterpret_cast<uint4*>(k_dst + dst_row * ldkv);
@@ -219,10 +242,9 @@ qk_norm_rope_kv_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
   }
   // v (plain copy into the cache)
   {
-    const uint4* r = reinterpret_cast<const uint4*>(v_in + static_cast<int64_t>(row) * ld_in);
     uint4* o = reinterpret_cast<uint4*>(v_dst + dst_row * ldkv);
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = r[lane + 32 * i];
+    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = kTogether ? vv[i] : rv[lane + 32 * i];
   }
 }
 

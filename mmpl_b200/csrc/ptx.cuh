@@ -247,6 +247,50 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
+// ------------------------------------------------------- packed fp32x2 math (sm_100)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for both halves on the FMA/ALU pipes instead of the MUFU: round-to-nearest split x = n + f with the
+// 1.5*2^23 trick, cubic minimax for 2^f on [-0.5, 0.5] (max relative error 1.0e-4, far below the bf16 rounding of
+// P), exponent inserted with an integer add. x is clamped to >= -125 so the exponent cannot wrap.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& out_lo, float& out_hi) {
+  float lo, hi;
+  unpack_f32x2(x2, lo, hi);
+  x2 = pack_f32x2(fmaxf(lo, -125.0f), fmaxf(hi, -125.0f));
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t t = add_f32x2(x2, magic);
+  const uint64_t f = sub_f32x2(x2, sub_f32x2(t, magic));
+  uint64_t p = fma_f32x2(f, pack_f32x2(0.05500871f, 0.05500871f), pack_f32x2(0.24221068f, 0.24221068f));
+  p = fma_f32x2(p, f, pack_f32x2(0.69328292f, 0.69328292f));
+  p = fma_f32x2(p, f, pack_f32x2(1.0f, 1.0f));
+  float plo, phi, tlo, thi;
+  unpack_f32x2(p, plo, phi);
+  unpack_f32x2(t, tlo, thi);
+  out_lo = __uint_as_float(__float_as_uint(plo) + (__float_as_uint(tlo) << 23));
+  out_hi = __uint_as_float(__float_as_uint(phi) + (__float_as_uint(thi) << 23));
+}
+
 // ------------------------------------------------------------------- misc
 // 32-byte (one full sector) global store / load; address must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
