@@ -203,3 +203,28 @@ def test_cfg2_full_size_properties():
                              timestep=torch.zeros(1, 3, device=DEV), kv_cache=pipe.kv_cache1,
                              crossattn_cache=pipe.crossattn_cache, current_start=18 * 1560)
     _cmp("cfg2 last-chunk flow (Lkv=32760)", flow[0], ref.permute(1, 0, 2, 3), 0.0625, 0.9999)
+
+
+def test_forward_14b_width_matches_oracle():
+    """Wan-14B width (dim 5120, 40 heads, ffn 13824), one block, small latents: exercises the D=5120 kernel
+    instantiations and the 40-head attention grid against the oracle on the same device."""
+    from mmpl_b200.causal_model import CausalWanModel
+    cfg = O.WanConfig(dim=5120, ffn_dim=13824, num_heads=40, num_layers=1)
+    w = O.make_weights(cfg, seed=9)
+    noise, prompt = _synth_inputs(cfg, 3, 16, 20)
+    model = CausalWanModel(dim=cfg.dim, ffn_dim=cfg.ffn_dim, num_heads=cfg.num_heads, num_layers=1)
+    model.load_state_dict(w)
+    model = model.to(DEV, torch.bfloat16).eval()
+    fs, rows = 8 * 10, 3 * 8 * 10 + 16
+    kv = [{"k": torch.zeros(1, rows, 40, 128, dtype=torch.bfloat16, device=DEV), "v": torch.zeros(1, rows, 40, 128, dtype=torch.bfloat16, device=DEV),
+           "global_end_index": torch.tensor([0], device=DEV), "local_end_index": torch.tensor([0], device=DEV)}]
+    cross = [{"k": None, "v": None, "is_init": False}]
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    okv, ocross = O.new_caches(cfg, rows, device=DEV)
+    x = noise.to(DEV)
+    t = torch.full((1, 3), 833.0, device=DEV)
+    flow = model(x.permute(0, 2, 1, 3, 4), t=t, context=prompt.to(DEV), seq_len=32760, kv_cache=kv, crossattn_cache=cross,
+                 current_start=0)
+    ref = O.model_forward(cfg, wd, x[0].permute(1, 0, 2, 3), t[0], prompt[0].to(DEV), okv, ocross, 0)
+    _cmp("14B-width flow", flow[0], ref, 0.0625, 0.9999)
+    _cmp("14B-width K cache", kv[0]["k"][0], okv[0].k, 0.0625, 0.9999)
