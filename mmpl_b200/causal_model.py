@@ -126,6 +126,8 @@ class CausalWanModel(nn.Module):
         self._fused: List[torch.Tensor] = []
         self._rope_table = None
         self._index_mirror: Dict[int, dict] = {}
+        self._param_list = None
+        self._qkv_list = None
         self.last_x0 = None
 
     # ------------------------------------------------------------------------------------------- init
@@ -154,7 +156,19 @@ class CausalWanModel(nn.Module):
             pass
 
     def _param_signature(self):
-        return tuple(p.data_ptr() for p in self.parameters()) + tuple(p._version for p in self.parameters())
+        """Cheap per-forward fingerprint of the bound parameters: storage pointers of every parameter (a `.to()` /
+        `.cuda()` moves them) and the version counters of the q/k/v projections (copied into the fused [3D, D] matrix,
+        so an in-place update such as load_state_dict must trigger a re-fuse)."""
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+            self._qkv_list = [t for blk in self.blocks for t in
+                              (blk.self_attn.q.weight, blk.self_attn.k.weight, blk.self_attn.v.weight,
+                               blk.self_attn.q.bias, blk.self_attn.k.bias, blk.self_attn.v.bias)]
+        return (tuple(p.data_ptr() for p in self._param_list), tuple(t._version for t in self._qkv_list))
+
+    def _apply(self, fn, *args, **kwargs):
+        self._param_list = None  # parameters may be replaced by .to() / .cuda()
+        return super()._apply(fn, *args, **kwargs)
 
     def _ensure_ctx(self, device: torch.device, tokens: int):
         lib = _lib.load()

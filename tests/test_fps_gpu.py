@@ -122,3 +122,37 @@ def test_fps_pipeline_runs_the_macro_from_micro_schedule():
     _, lat_i = pipe_i.inference(noise=noise, text_prompts=["p"], initial_latent=first, return_latents=True)
     assert torch.equal(lat_i[:, :1], first) and anchors_i[0].shape == (1, 3, 16, 16, 24)
     assert torch.equal(anchors_i[0], lat_i[:, [0, 19, 20]]) and torch.isfinite(lat_i.float()).all()
+
+
+def test_cfg_diffusion_pipeline_on_gpu():
+    """CausalDiffusionInferencePipeline mirror end to end on the contiguous-cache model: indices of both caches
+    advance by one chunk per chunk, output finite and reproducible."""
+    from mmpl_b200.causal_model import CausalWanModel
+    from mmpl_b200.pipeline import CausalDiffusionInferencePipeline
+    from mmpl_b200.wan_wrapper import WanDiffusionWrapper
+    cfg = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
+    m = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
+                       num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+    m.load_state_dict(O.make_weights(cfg, 4))
+    gen = WanDiffusionWrapper(model=m.to(DEV, torch.bfloat16).eval(), timestep_shift=5.0)
+    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(DEV)
+
+    class Text(torch.nn.Module):
+        def forward(self, text_prompts):
+            return {"prompt_embeds": prompt if text_prompts[0] != "neg" else -prompt}
+
+    class VAE(torch.nn.Module):
+        def decode_to_pixel(self, latents, use_cache=False):
+            return latents
+
+    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="neg",
+                                 independent_first_frame=False, num_frame_per_block=3, sampling_steps=3, model_kwargs={})
+    pipe = CausalDiffusionInferencePipeline(args, DEV, generator=gen, text_encoder=Text(), vae=VAE())
+    noise = torch.randn(1, 6, 16, 16, 24, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).to(DEV)
+    _, lat = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
+    fs = 8 * 12
+    for cache in (pipe.kv_cache_pos, pipe.kv_cache_neg):
+        assert int(cache[0]["global_end_index"]) == int(cache[-1]["local_end_index"]) == 6 * fs
+    assert torch.isfinite(lat.float()).all() and lat.float().abs().mean() > 0
+    _, lat2 = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
+    assert torch.equal(lat, lat2)

@@ -80,3 +80,33 @@ def test_initial_latent_prefill_calls():
     _, latents = pipe.inference(noise=noise, text_prompts=["p"], initial_latent=init, return_latents=True)
     assert latents.shape[1] == 6 and torch.equal(latents[:, :3], init)
     assert gen.calls[0][:2] == (0, 0.0) and gen.calls[1][:2] == (3 * 24, 1000.0) and len(gen.calls) == 6
+
+
+def test_cfg_diffusion_pipeline_schedule():
+    """CausalDiffusionInferencePipeline (pipeline/causal_diffusion_inference.py): per chunk, `steps` x (cond, uncond)
+    forwards followed by the clean-context pass on both caches; contiguous current_start; separate pos/neg caches."""
+    from mmpl_b200.pipeline import CausalDiffusionInferencePipeline
+    gen = FakeGenerator()
+    calls = []
+
+    def fwd(noisy_image_or_video, conditional_dict, timestep, kv_cache, crossattn_cache, current_start, cache_start):
+        calls.append((conditional_dict["tag"], int(current_start), float(timestep.flatten()[0]), id(kv_cache)))
+        return noisy_image_or_video * 0.1, None
+
+    gen.forward = fwd
+    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="neg",
+                                 independent_first_frame=False, num_frame_per_block=3, sampling_steps=3, model_kwargs={})
+    text = lambda text_prompts: {"tag": "neg" if text_prompts[0] == "neg" else "pos"}  # noqa: E731
+    vae = types.SimpleNamespace(decode_to_pixel=lambda latents: latents)
+    pipe = CausalDiffusionInferencePipeline(args, torch.device("cpu"), generator=gen, text_encoder=text, vae=vae)
+    noise = torch.randn(1, 6, 16, 8, 12, generator=torch.Generator().manual_seed(0))
+    _, lat = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
+    fs = 24
+    steps = [float(t) for t in pipe.timesteps]
+    assert len(steps) == 3 and steps == sorted(steps, reverse=True)
+    expect = []
+    for chunk in range(2):
+        for t in steps + [0.0]:
+            expect += [("pos", chunk * 3 * fs, t), ("neg", chunk * 3 * fs, t)]
+    assert [c[:3] for c in calls] == expect
+    assert len({c[3] for c in calls}) == 2 and lat.shape == noise.shape and torch.isfinite(lat).all()
