@@ -7,6 +7,7 @@ if the shared library is missing (and cannot be built) loading raises, there is 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import _build
@@ -91,6 +92,9 @@ def load(build_if_missing: bool = True):
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
+    override = os.environ.get("MMPL_B200_LIB")  # A/B runs of tools/bench_kernels.py against another build
+    if override:
+        path, build_if_missing = Path(override), False
     if build_if_missing and _build.is_stale():
         try:
             _build.build_library()

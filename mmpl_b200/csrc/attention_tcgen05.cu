@@ -24,6 +24,7 @@
 // first 64 columns of S_q. O is rescaled lazily (only when the running max grows by > 2^8), by the
 // softmax warps themselves.
 #include <cstdlib>
+#include <type_traits>
 
 #include "host_util.h"
 #include "mmpl_b200.h"
@@ -35,6 +36,24 @@
 #endif
 #ifndef MMPL_ATTN_HALVES
 #define MMPL_ATTN_HALVES 0
+#endif
+#ifndef MMPL_ATTN_STALE_MAX
+#define MMPL_ATTN_STALE_MAX 0
+#endif
+
+#ifndef MMPL_ATTN_TIMING
+#define MMPL_ATTN_TIMING 0
+#endif
+#if MMPL_ATTN_TIMING
+// Development build only (tools/attn_timing.py): per-phase clock64() totals of CTA 0.
+//   [qt*4 + 0..3] softmax warp of query tile qt: waiting for S, computing P, storing P + arrive, tiles
+//   [8 + qt] MMA warp waiting for P_qt   [10] waiting for V   [11] waiting for K   [12] MMA warp total   [13] tiles
+__device__ long long g_attn_dbg[32];
+#define TSTAMP(var) const long long var = clock64()
+#define TACC(slot, val) dbg[slot] += (val)
+#else
+#define TSTAMP(var)
+#define TACC(slot, val)
 #endif
 
 namespace mmpl {
@@ -65,6 +84,12 @@ constexpr int kUnitRows = 2 * kQTile;
 #endif
 constexpr int kPolyNum = MMPL_ATTN_POLY_NUM;  // pairs per kPolyDen whose exp2 runs on the FMA/ALU pipes
 constexpr int kPolyDen = 16;
+// Which of every 16 element pairs take the polynomial path: alternating with the MUFU pairs in program order, so that
+// the FMA-pipe work of a polynomial pair issues in the shadow of the 8-clk MUFU instructions next to it (ptxas keeps
+// close to source order; with the polynomial pairs bunched at the front of each group the two pipes took turns).
+__host__ __device__ constexpr bool pair_is_poly(int i) {
+  return ((i % kPolyDen) & 1) == 0 && (i % kPolyDen) < 2 * kPolyNum;
+}
 
 struct AttnParams {
   int Lq, H;
@@ -198,21 +223,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: everything above overlapped the tail of the previous kernel; Q/K/V are valid from here on
+  pdl_launch_dependents();
 
   if (warp < kFirstSoftmaxWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MMPL_ATTN_CTRL_REGS));
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // -------------------------------------------------------- TMA producer
+      // (whole warp, converged; one elected lane issues each TMA: see the "_elect" wrappers in ptx.cuh)
       int g = 0, piece = 0;
       for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
         const Piece pc = piece_info(p, pi);
         const int t0 = pc.t0, n = pc.n, head = pc.head, q_row0 = pc.q_row0;
         mbar_wait(q_empty, (piece & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, 4 * kBoxBytes);
+        mbar_arrive_expect_tx_elect(q_full, 4 * kBoxBytes);
         for (int qt = 0; qt < 2; ++qt)
           for (int hh = 0; hh < 2; ++hh)
-            tma_load_2d(smem_q + (qt * 2 + hh) * kBoxBytes, &map_q, q_full, head * kHD + hh * 64,
-                        q_row0 + qt * kQTile, kEvictFirst);
+            tma_load_2d_elect(smem_q + (qt * 2 + hh) * kBoxBytes, &map_q, q_full, head * kHD + hh * 64,
+                              q_row0 + qt * kQTile, kEvictFirst);
         TileIter it;
         it.init(p, t0);
         for (int jj = 0; jj < n; ++jj, ++g, it.next(p)) {
@@ -221,13 +249,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const int st = g & 1;
           const uint32_t ph = (g >> 1) & 1;
           mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], 2 * kBoxBytes);
+          mbar_arrive_expect_tx_elect(&k_full[st], 2 * kBoxBytes);
           for (int hh = 0; hh < 2; ++hh)
-            tma_load_2d(smem_k + (st * 2 + hh) * kBoxBytes, mk, &k_full[st], head * kHD + hh * 64, it.row, kEvictLast);
+            tma_load_2d_elect(smem_k + (st * 2 + hh) * kBoxBytes, mk, &k_full[st], head * kHD + hh * 64, it.row, kEvictLast);
           mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], 2 * kBoxBytes);
+          mbar_arrive_expect_tx_elect(&v_full[st], 2 * kBoxBytes);
           for (int hh = 0; hh < 2; ++hh)
-            tma_load_2d(smem_v + (st * 2 + hh) * kBoxBytes, mv, &v_full[st], head * kHD + hh * 64, it.row, kEvictLast);
+            tma_load_2d_elect(smem_v + (st * 2 + hh) * kBoxBytes, mv, &v_full[st], head * kHD + hh * 64, it.row, kEvictLast);
         }
       }
     } else if (warp == 1) {
@@ -239,49 +267,57 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const uint32_t v_addr = smem_u32(smem_v);
 
       // S_q = Q_q . K(stage)^T : 8 k-steps of 16 over head_dim (two 64-wide swizzled halves)
+      // (every lane runs the issue code, one elected lane issues each tcgen05 instruction: ptx.cuh "_elect" wrappers;
+      //  descriptors = constant high word + (smem address >> 4) in the low word)
+      constexpr uint64_t kDescK = make_smem_desc_sw128_const(16, 1024);          // K-major Q / K tiles
+      constexpr uint64_t kDescV = make_smem_desc_sw128_const(kBoxBytes, 1024);   // MN-major V tile
       auto issue_qk = [&](int qt, int st) {
+        const uint32_t a0 = desc_lo(kDescK) + ((q_addr + qt * 2 * kBoxBytes) >> 4);
+        const uint32_t b0 = desc_lo(kDescK) + ((k_addr + st * 2 * kBoxBytes) >> 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int hh = k >> 2;
-          const uint64_t da = make_smem_desc_sw128(q_addr + (qt * 2 + hh) * kBoxBytes, 16, 1024) + 2 * (k & 3);
-          const uint64_t db = make_smem_desc_sw128(k_addr + (st * 2 + hh) * kBoxBytes, 16, 1024) + 2 * (k & 3);
-          umma_ss(tmem_base + qt * 128, da, db, idesc_qk, k != 0 ? 1u : 0u);
+          const uint32_t off = (k >> 2) * (kBoxBytes >> 4) + 2 * (k & 3);
+          umma_ss_elect(tmem_base + qt * 128, a0 + off, desc_hi(kDescK), b0 + off, desc_hi(kDescK), idesc_qk, k != 0 ? 1u : 0u);
         }
       };
       // O_q += P_q . V(stage) : 8 k-steps of 16 kv rows; V is MN-major (hd contiguous), the two
       // 64-wide hd halves are 16 KB apart (LBO), 8-row kv groups 1 KB apart (SBO).
       auto issue_pv = [&](int qt, int st, int half, bool first) {
 #pragma unroll
+        const uint32_t b0 = desc_lo(kDescV) + ((v_addr + st * 2 * kBoxBytes) >> 4);
         for (int kk = 0; kk < 4; ++kk) {
           const int k = half * 4 + kk;
-          const uint64_t db = make_smem_desc_sw128(v_addr + st * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-          umma_ts(tmem_base + 256 + qt * 128, tmem_base + qt * 128 + 8 * k, db, idesc_pv,
-                  (first && k == 0) ? 0u : 1u);
+          umma_ts_elect(tmem_base + 256 + qt * 128, tmem_base + qt * 128 + 8 * k, b0 + k * (2048 >> 4), desc_hi(kDescV),
+                        idesc_pv, (first && k == 0) ? 0u : 1u);
         }
       };
 
+#if MMPL_ATTN_TIMING
+      long long dbg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const long long tm_begin = clock64();
+#endif
       int g = 0, piece = 0;
       for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
         const int n = piece_info(p, pi).n;
         mbar_wait(q_full, piece & 1);
         mbar_wait(&k_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          issue_qk(0, g & 1);
-          tc_commit(&s_full[0]);
-          issue_qk(1, g & 1);
-          tc_commit(&s_full[1]);
-          tc_commit(&k_empty[g & 1]);
-          if (n == 1) tc_commit(q_empty);
-        }
-        __syncwarp();
+        issue_qk(0, g & 1);
+        tc_commit_elect(&s_full[0]);
+        issue_qk(1, g & 1);
+        tc_commit_elect(&s_full[1]);
+        tc_commit_elect(&k_empty[g & 1]);
+        if (n == 1) tc_commit_elect(q_empty);
         for (int jj = 0; jj < n; ++jj) {
           const int gj = g + jj;
           const int st = gj & 1;
           const uint32_t ph = (gj >> 1) & 1;
           const int stn = (gj + 1) & 1;
           const uint32_t phn = ((gj + 1) >> 1) & 1;
+          TSTAMP(tv0);
           mbar_wait(&v_full[st], ph);
+          TSTAMP(tv1);
+          TACC(10, tv1 - tv0); TACC(13, 1);
           for (int qt = 0; qt < 2; ++qt) {
             // P arrives in two halves (KV rows 0-63, 64-127) so that P.V starts while the second half is still
             // being exponentiated
@@ -289,37 +325,42 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mbar_wait(&p_full[2 * qt], gj & 1);
             if (jj == 0) mbar_wait(&o_empty[qt], (piece & 1) ^ 1);  // previous piece's O has been read out
             tc_fence_after();
-            if (lane == 0) issue_pv(qt, st, 0, jj == 0);
-            __syncwarp();
+            issue_pv(qt, st, 0, jj == 0);
             mbar_wait(&p_full[2 * qt + 1], gj & 1);
 #else
+            TSTAMP(tp0);
             mbar_wait(&p_full[2 * qt + 1], gj & 1);
+            TSTAMP(tp1);
+            TACC(8 + qt, tp1 - tp0);
             if (jj == 0) mbar_wait(&o_empty[qt], (piece & 1) ^ 1);
             tc_fence_after();
-            if (lane == 0) issue_pv(qt, st, 0, jj == 0);
-            __syncwarp();
+            issue_pv(qt, st, 0, jj == 0);
 #endif
+            TSTAMP(tk0);
             if (qt == 0 && jj + 1 < n) mbar_wait(&k_full[stn], phn);
+            TSTAMP(tk1);
+            TACC(11, tk1 - tk0);
             tc_fence_after();
-            if (lane == 0) {
-              issue_pv(qt, st, 1, false);
-              if (qt == 1) tc_commit(&v_empty[st]);
-              if (jj + 1 < n) {
-                issue_qk(qt, stn);
-                tc_commit(&s_full[qt]);
-                if (qt == 1) {
-                  tc_commit(&k_empty[stn]);
-                  if (jj + 2 == n) tc_commit(q_empty);  // last QK of the piece issued: Q smem may be reloaded
-                }
+            issue_pv(qt, st, 1, false);
+            if (qt == 1) tc_commit_elect(&v_empty[st]);
+            if (jj + 1 < n) {
+              issue_qk(qt, stn);
+              tc_commit_elect(&s_full[qt]);
+              if (qt == 1) {
+                tc_commit_elect(&k_empty[stn]);
+                if (jj + 2 == n) tc_commit_elect(q_empty);  // last QK of the piece issued: Q smem may be reloaded
               }
             }
-            __syncwarp();
           }
         }
-        if (lane == 0) tc_commit(o_full);
-        __syncwarp();
+        tc_commit_elect(o_full);
         g += n;
       }
+#if MMPL_ATTN_TIMING
+      dbg[12] = clock64() - tm_begin;
+      if (blockIdx.x == 0 && lane == 0)
+        for (int i = 8; i < 14; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&g_attn_dbg[i]), (unsigned long long)dbg[i]);
+#endif
     }
   } else {
     // ------------------------------------------------------------- softmax
@@ -330,6 +371,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t t_s = tmem_base + t_lane + qt * 128;
     const uint32_t t_o = tmem_base + t_lane + 256 + qt * 128;
     const int row_in_unit = qt * kQTile + lane_base + lane;
+#if MMPL_ATTN_TIMING
+    long long dbg[4] = {0, 0, 0, 0};
+#endif
     int g = 0, piece = 0;
     for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
       const Piece pc = piece_info(p, pi);
@@ -339,10 +383,116 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       float l_run = 0.f;
       TileIter it;
       it.init(p, t0);
+#if MMPL_ATTN_STALE_MAX
+      // One pass over the 128 scores of this row, 32 columns at a time; the tcgen05.ld of chunk c+1 is in flight while
+      // chunk c is processed. kMaxOnly: row maximum only. Otherwise P = 2^(S*scale - m_run) with the running maximum of
+      // the PREVIOUS tiles (the row maximum of this tile is gathered on the side, on the ALU pipe): the exponentials do
+      // not wait for a max pass over the tile. The caller checks afterwards whether the maximum grew by more than the
+      // lazy-rescale threshold and, in that rare case, repeats the pass (S is still intact in TMEM: P is stored later).
+      uint32_t pk[64];
+      float mx_tile, sum_tile;
+      auto pass = [&](auto max_only_tag, int valid) {
+        constexpr bool kMaxOnly = decltype(max_only_tag)::value;
+        float mxk[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        uint64_t sumk[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
+        uint32_t sva[32], svb[32];
+        auto chunk = [&](uint32_t (&sv)[32], int c) {
+          if (valid < kKVTile) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sv[i] = 0xFF800000u;  // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            mxk[i & 3] = fmaxf(fmaxf(mxk[i & 3], __uint_as_float(sv[2 * i])), __uint_as_float(sv[2 * i + 1]));
+          if (!kMaxOnly) {
+            // packed fp32x2 FMA for the scaling and the row sum; kPolyNum of every kPolyDen pairs are exponentiated on
+            // the FMA/ALU pipes (exp2_poly_x2) instead of the MUFU (16 ex2/clk/SM against 128 x 128 per tile).
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
+              float p0, p1;
+              if (pair_is_poly(i)) {
+                exp2_poly_x2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                p0 = fast_exp2(x0);
+                p1 = fast_exp2(x1);
+              }
+              sumk[i & 1] = add_f32x2(sumk[i & 1], pack_f32x2(p0, p1));
+              pk[c * 16 + i] = pack_bf16x2(p0, p1);
+            }
+          }
+        };
+        tmem_ld_32x32(t_s, sva);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 32, svb);
+        chunk(sva, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 64, sva);
+        chunk(svb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 96, svb);
+        chunk(sva, 2);
+        tmem_ld_wait();
+        chunk(svb, 3);
+        mx_tile = fmaxf(fmaxf(mxk[0], mxk[1]), fmaxf(mxk[2], mxk[3]));
+        float s_lo, s_hi;
+        unpack_f32x2(add_f32x2(sumk[0], sumk[1]), s_lo, s_hi);
+        sum_tile = s_lo + s_hi;
+      };
       for (int jj = 0; jj < n; ++jj, it.next(p)) {
         const int valid = it.valid();
+        TSTAMP(ts0);
         mbar_wait(&s_full[qt], (g + jj) & 1);
         tc_fence_after();
+        TSTAMP(ts1);
+        if (jj == 0) {  // no running maximum yet: take it from this tile
+          pass(std::true_type{}, valid);
+          m_run = mx_tile * p.scale_log2;
+        }
+        for (;;) {
+          pass(std::false_type{}, valid);
+          const float m_new = fmaxf(m_run, mx_tile * p.scale_log2);
+          const bool grow = m_new > m_run + 8.0f;
+          if (!__any_sync(0xffffffffu, grow)) break;
+          // the maximum grew by more than 2^8 somewhere in this warp: rescale l and O, then redo the tile
+          const float alpha = fast_exp2(m_run - m_new);
+          l_run *= alpha;
+          m_run = m_new;
+          if (jj > 0) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32(t_o + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32(t_o + c * 32, o);
+            }
+          }
+        }
+        TSTAMP(ts2);
+        tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * qt + 1]);
+        l_run += sum_tile;
+        TSTAMP(ts3);
+        TACC(0, ts1 - ts0); TACC(1, ts2 - ts1); TACC(2, ts3 - ts2); TACC(3, 1);
+      }
+#else
+      for (int jj = 0; jj < n; ++jj, it.next(p)) {
+        const int valid = it.valid();
+        TSTAMP(ts0);
+        mbar_wait(&s_full[qt], (g + jj) & 1);
+        tc_fence_after();
+        TSTAMP(ts1);
         uint32_t sv[128];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
@@ -352,9 +502,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int c = 0; c < 128; ++c)
             if (c >= valid) sv[c] = 0xFF800000u;  // -inf
         }
-        float mx = __uint_as_float(sv[0]);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains of 3-input max
 #pragma unroll
-        for (int c = 1; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+        for (int c = 0; c < 64; ++c)
+          mx4[c & 3] = fmaxf(fmaxf(mx4[c & 3], __uint_as_float(sv[2 * c])), __uint_as_float(sv[2 * c + 1]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
         const bool grow = m_new > m_run + 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
@@ -384,7 +536,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int c = 0; c < 64; ++c) {
           const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sc2, nm2);
           float p0, p1;
-          if ((c % kPolyDen) < kPolyNum) {
+          if (pair_is_poly(c)) {
             exp2_poly_x2(x2, p0, p1);
           } else {
             float x0, x1;
@@ -401,6 +553,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           unpack_f32x2(sum2, s_lo, s_hi);
           sum = s_lo + s_hi;
         }
+        TSTAMP(ts2);
         tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
 #if MMPL_ATTN_HALVES
         tmem_st_wait();
@@ -414,7 +567,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[2 * qt + 1]);
         l_run += sum;
+        TSTAMP(ts3);
+        TACC(0, ts1 - ts0); TACC(1, ts2 - ts1); TACC(2, ts3 - ts2); TACC(3, 1);
       }
+#endif
       // piece epilogue
       mbar_wait(o_full, piece & 1);
       tc_fence_after();
@@ -467,6 +623,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       if (lane == 0) mbar_arrive(&o_empty[qt]);
       g += n;
     }
+#if MMPL_ATTN_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
+      for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&g_attn_dbg[qt * 4 + i]), (unsigned long long)dbg[i]);
+#endif
   }
 
   tc_fence_before();
@@ -481,6 +641,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 //   out = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i,  M = max_i m_i.   One warp per query row.
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int u = blockIdx.x >> 5;
   const int row_in_unit = (blockIdx.x & 31) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -587,14 +749,26 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
     MMPL_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
-  flash_attn_kernel<<<G, kAttnThreads, kAttnSmem, stream>>>(*mq, *mk0, *mv0, *mk1, *mv1, p);
+  MMPL_CUDA_LAUNCH(launch_kernel(flash_attn_kernel, G, kAttnThreads, kAttnSmem, stream, *mq, *mk0, *mv0, *mk1, *mv1, p));
   MMPL_CUDA(cudaGetLastError());
   if (p.split > 1) {
-    attn_combine_kernel<<<U * 32, 256, 0, stream>>>(p);
+    MMPL_CUDA_LAUNCH(launch_kernel(attn_combine_kernel, U * 32, 256, 0, stream, p));
     MMPL_CUDA(cudaGetLastError());
   }
   return MMPL_OK;
 }
+
+#if MMPL_ATTN_TIMING
+extern "C" int mmpl_attn_debug_read(long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_attn_dbg, sizeof(long long) * 32);
+  if (reset) {
+    long long z[32] = {0};
+    cudaMemcpyToSymbol(g_attn_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 }  // namespace MMPL_ATTN_NS
 }  // namespace mmpl

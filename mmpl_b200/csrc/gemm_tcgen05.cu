@@ -10,7 +10,8 @@
 //   EPI_BIAS_RES       bf16(res + y)                              (cross-attn residual, :314)
 //   EPI_BIAS_GATE_RES  bf16(res + bf16(y * gate[frame(row)]))     (:310, :322)
 //
-// Structure: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue.
+// Structure: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..9 = epilogue (warps 2-5 take the
+// left half of the tile's columns, warps 6-9 the right half: two warps per scheduler hide each other's latencies).
 // A/W tiles are [128|BN rows] x [64 k] bf16 boxes in 128B-swizzled smem; the 128 x BN fp32
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "host_util.h"
@@ -21,7 +22,8 @@ namespace mmpl {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kEpiWarps = 8;
 
 struct GemmParams {
   int M, N, K;
@@ -46,59 +48,75 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// gelu_tanh(x) = 0.5 x (1 + tanh(u)) = x * sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3):
+// one ex2 and one rcp on the MUFU and five FMA-pipe operations per element.
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
-  const float kKappa = 0.044715f;
-  float inner = kBeta * (x + kKappa * x * x * x);
-  // tanh(u) = 1 - 2 / (exp(2u) + 1)
-  float t = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
-  return 0.5f * x * (1.0f + t);
+  const float kK = -2.0f * 1.4426950408889634f * 0.7978845608028654f;  // -2 log2(e) sqrt(2/pi)
+  const float w = fmaf(x * x, kK * 0.044715f, kK);
+  const float e = fast_exp2(x * w);  // exp(-2u)
+  return __fdividef(x, 1.0f + e);
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // Epilogue of one accumulator row: `taddr` addresses this warp's 32 TMEM lanes at the tile's first column; the
 // thread owns output row `row`, columns [col_base, col_base + BN). Rounds to bf16 where the reference does.
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int col_base) {
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int col_base, int c_begin,
+                                              int c_end) {
+  constexpr bool kHasRes = (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES);
   const bool row_ok = row < p.M;
   const __nv_bfloat16* gate_row = nullptr;
   if (EPI == MMPL_EPI_BIAS_GATE_RES && row_ok)
     gate_row = p.gate + static_cast<int64_t>(row / p.rows_per_frame) * p.gate_stride;
+  // N is a multiple of 8: 8-column (16-byte) groups; two groups are stored together as one 32-byte sector
+  // (st.global.v8) when the row pitch allows, so no sector is written partially.
+  const bool wide = (p.ldo % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0);
+  const bool wide_res = kHasRes && (p.ldr % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 31) == 0);
+  // Residual of one 32-column chunk of this thread's row (64 bytes); loaded one chunk AHEAD of its use, so that the
+  // global-load latency overlaps the tcgen05.ld and the arithmetic of the previous chunk instead of adding to every chunk.
+  auto load_res = [&](int c, uint32_t (&r)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0;
+    const int col0 = col_base + c * 32;
+    if (!kHasRes || !row_ok || col0 >= p.N) return;
+    const __nv_bfloat16* src = p.res + static_cast<int64_t>(row) * p.ldr + col0;
+#pragma unroll
+    for (int g2 = 0; g2 < 2; ++g2) {
+      if (col0 + g2 * 16 + 16 <= p.N && wide_res) {
+        asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[g2 * 8]), "=r"(r[g2 * 8 + 1]), "=r"(r[g2 * 8 + 2]), "=r"(r[g2 * 8 + 3]), "=r"(r[g2 * 8 + 4]),
+                       "=r"(r[g2 * 8 + 5]), "=r"(r[g2 * 8 + 6]), "=r"(r[g2 * 8 + 7])
+                     : "l"(src + g2 * 16)
+                     : "memory");
+      } else {
+        if (col0 + g2 * 16 < p.N) {
+          const uint4 t = *reinterpret_cast<const uint4*>(src + g2 * 16);
+          r[g2 * 8] = t.x; r[g2 * 8 + 1] = t.y; r[g2 * 8 + 2] = t.z; r[g2 * 8 + 3] = t.w;
+        }
+        if (col0 + g2 * 16 + 8 < p.N) {
+          const uint4 t = *reinterpret_cast<const uint4*>(src + g2 * 16 + 8);
+          r[g2 * 8 + 4] = t.x; r[g2 * 8 + 5] = t.y; r[g2 * 8 + 6] = t.z; r[g2 * 8 + 7] = t.w;
+        }
+      }
+    }
+  };
+  uint32_t res_next[16];
+  load_res(c_begin, res_next);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t acc[32];
     tmem_ld_32x32(taddr + c * 32, acc);
+    uint32_t rres[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rres[i] = res_next[i];
+    if (kHasRes && c + 1 < c_end) load_res(c + 1, res_next);
     tmem_ld_wait();
     const int col0 = col_base + c * 32;
     if (row_ok && col0 < p.N) {
-      // N is a multiple of 8: 8-column (16-byte) groups; two groups are stored together as one 32-byte sector
-      // (st.global.v8) when the row pitch allows, so no sector is written partially.
-      const bool wide = (p.ldo % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0);
 #pragma unroll
       for (int g2 = 0; g2 < 2; ++g2) {
         uint32_t ow[8];
         bool have[2] = {false, false};
-        // residual: one 32-byte load per 16 columns when the layout allows it
-        uint32_t rres[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES) {
-          const __nv_bfloat16* src = p.res + static_cast<int64_t>(row) * p.ldr + col0 + g2 * 16;
-          if (col0 + g2 * 16 + 16 <= p.N && (p.ldr % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 31) == 0)) {
-            asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(rres[0]), "=r"(rres[1]), "=r"(rres[2]), "=r"(rres[3]), "=r"(rres[4]), "=r"(rres[5]),
-                           "=r"(rres[6]), "=r"(rres[7])
-                         : "l"(src)
-                         : "memory");
-          } else {
-            if (col0 + g2 * 16 < p.N) {
-              const uint4 t = *reinterpret_cast<const uint4*>(src);
-              rres[0] = t.x; rres[1] = t.y; rres[2] = t.z; rres[3] = t.w;
-            }
-            if (col0 + g2 * 16 + 8 < p.N) {
-              const uint4 t = *reinterpret_cast<const uint4*>(src + 8);
-              rres[4] = t.x; rres[5] = t.y; rres[6] = t.z; rres[7] = t.w;
-            }
-          }
-        }
 #pragma unroll
         for (int gg = 0; gg < 2; ++gg) {
           const int g = g2 * 2 + gg;
@@ -107,11 +125,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
           have[gg] = true;
           uint4 bv = make_uint4(0, 0, 0, 0);
           if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-          uint4 rv = make_uint4(rres[gg * 4], rres[gg * 4 + 1], rres[gg * 4 + 2], rres[gg * 4 + 3]), gv = make_uint4(0, 0, 0, 0);
+          uint4 gv = make_uint4(0, 0, 0, 0);
           if (EPI == MMPL_EPI_BIAS_GATE_RES)
             gv = __ldg(reinterpret_cast<const uint4*>(gate_row + col));
           const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+          const uint32_t* rw = &rres[g * 4];
           const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -135,9 +153,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         }
         __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0 + g2 * 16;
         if (have[0] && have[1] && wide) {
-          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(ow[0]), "r"(ow[1]),
-                       "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
-                       : "memory");
+          st_global_v8(dst, ow);
         } else {
           if (have[0]) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           if (have[1]) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
@@ -181,7 +197,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full[i], 1);
-        mbar_init(&tmem_empty[i], 4);
+        mbar_init(&tmem_empty[i], kEpiWarps);
       }
       fence_mbar_init();
     }
@@ -193,22 +209,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: the prologue above overlapped the previous kernel; its outputs (A, residual) are valid from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t % p.tiles_m;
-        const int n_blk = t / p.tiles_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_2d(smem_a + s * Cfg::kABytes, &map_a, &full_bar[s], kb * kBK, m_blk * kBM, kEvictNormal);
-          tma_load_2d(smem_b + s * Cfg::kBBytes, &map_b, &full_bar[s], kb * kBK, n_blk * BN, kEvictLast);
-          if (++s == ST) { s = 0; ph ^= 1; }
-        }
+    // (whole warp, converged; one elected lane issues: see the "_elect" wrappers in ptx.cuh)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t % p.tiles_m;
+      const int n_blk = t / p.tiles_m;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx_elect(&full_bar[s], Cfg::kStageBytes);
+        tma_load_2d_elect(smem_a + s * Cfg::kABytes, &map_a, &full_bar[s], kb * kBK, m_blk * kBM, kEvictNormal);
+        tma_load_2d_elect(smem_b + s * Cfg::kBBytes, &map_b, &full_bar[s], kb * kBK, n_blk * BN, kEvictLast);
+        if (++s == ST) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -226,18 +243,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * Cfg::kABytes), 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * Cfg::kBBytes), 16, 1024);
+        // descriptor = constant high word + start address (>> 4) in the low word
+        constexpr uint64_t kDesc0 = make_smem_desc_sw128_const(16, 1024);
+        const uint32_t a_lo = desc_lo(kDesc0) + ((smem_u32(smem_a) + s * Cfg::kABytes) >> 4);
+        const uint32_t b_lo = desc_lo(kDesc0) + ((smem_u32(smem_b) + s * Cfg::kBBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes (= 2 in the >>4 address field) per 16-element K step inside the swizzle atom
-            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(&empty_bar[s]);
-          if (kb == num_kb - 1) tc_commit(&tmem_full[as]);
+        for (int k = 0; k < kBK / 16; ++k) {
+          // +32 bytes (= 2 in the >>4 address field) per 16-element K step inside the swizzle atom
+          umma_ss_elect(tmem_d, a_lo + 2 * k, desc_hi(kDesc0), b_lo + 2 * k, desc_hi(kDesc0), idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        __syncwarp();
+        tc_commit_elect(&empty_bar[s]);
+        if (kb == num_kb - 1) tc_commit_elect(&tmem_full[as]);
         if (++s == ST) { s = 0; ph ^= 1; }
       }
     }
@@ -253,7 +269,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const int row = m_blk * kBM + lane_base + lane;
-      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN);
+      constexpr int kChunks = BN / 32 / 2;  // 32-column chunks per warp
+      const int half = (warp - 2) >> 2;
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
+                             half * kChunks, (half + 1) * kChunks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -320,7 +339,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full[i], 1);
-        mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs
+        mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // epilogue warps of both CTAs
       }
       fence_mbar_init();
     }
@@ -332,24 +351,24 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL (see above)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs, own halves)
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int m_blk = t % p.tiles_m;
-        const int n_blk = t / p.tiles_m;
-        const int row_a = m_blk * 256 + static_cast<int>(cta) * kBM;
-        const int row_b = n_blk * BN + static_cast<int>(cta) * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kPairStageBytes);
-          tma_load_2d_2cta(smem_a + s * (kPairStageBytes / 2), &map_a, &full_bar[s], kb * kBK, row_a, kEvictNormal);
-          tma_load_2d_2cta(smem_b + s * (kPairStageBytes / 2), &map_b, &full_bar[s], kb * kBK, row_b, kEvictLast);
-          if (++s == ST) { s = 0; ph ^= 1; }
-        }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = t % p.tiles_m;
+      const int n_blk = t / p.tiles_m;
+      const int row_a = m_blk * 256 + static_cast<int>(cta) * kBM;
+      const int row_b = n_blk * BN + static_cast<int>(cta) * (BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader) mbar_arrive_expect_tx_elect(&full_bar[s], 2 * kPairStageBytes);
+        tma_load_2d_2cta_elect(smem_a + s * (kPairStageBytes / 2), &map_a, &full_bar[s], kb * kBK, row_a, kEvictNormal);
+        tma_load_2d_2cta_elect(smem_b + s * (kPairStageBytes / 2), &map_b, &full_bar[s], kb * kBK, row_b, kEvictLast);
+        if (++s == ST) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -368,16 +387,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * (kPairStageBytes / 2)), 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * (kPairStageBytes / 2)), 16, 1024);
+          constexpr uint64_t kDesc0 = make_smem_desc_sw128_const(16, 1024);
+          const uint32_t a_lo = desc_lo(kDesc0) + ((smem_u32(smem_a) + s * (kPairStageBytes / 2)) >> 4);
+          const uint32_t b_lo = desc_lo(kDesc0) + ((smem_u32(smem_b) + s * (kPairStageBytes / 2)) >> 4);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            tc_commit_2cta(&empty_bar[s], 0x3);
-            if (kb == num_kb - 1) tc_commit_2cta(&tmem_full[as], 0x3);
-          }
-          __syncwarp();
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_ss_2cta_elect(tmem_d, a_lo + 2 * k, desc_hi(kDesc0), b_lo + 2 * k, desc_hi(kDesc0), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+          tc_commit_2cta_elect(&empty_bar[s], 0x3);
+          if (kb == num_kb - 1) tc_commit_2cta_elect(&tmem_full[as], 0x3);
           if (++s == ST) { s = 0; ph ^= 1; }
         }
       }
@@ -394,7 +412,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(cta) * kBM + lane_base + lane;
-      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN);
+      constexpr int kChunks = BN / 32 / 2;
+      const int half = (warp - 2) >> 2;
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
+                             half * kChunks, (half + 1) * kChunks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
@@ -422,7 +443,7 @@ static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmPa
   const int tiles = p.tiles_m * p.tiles_n;
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kern<<<2 * pairs, kGemmThreads, kPairSmemBytes, stream>>>(*ma, *mb, p);
+  MMPL_CUDA_LAUNCH(launch_kernel(kern, 2 * pairs, kGemmThreads, kPairSmemBytes, stream, *ma, *mb, p));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -452,7 +473,7 @@ static int launch_gemm(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams 
   p.tiles_n = (p.N + BN - 1) / BN;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*ma, *mb, p);
+  MMPL_CUDA_LAUNCH(launch_kernel(kern, grid, kGemmThreads, Cfg::kSmemBytes, stream, *ma, *mb, p));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }

@@ -1,5 +1,7 @@
 #include "host_util.h"
 
+#include <cstdlib>
+
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -116,6 +118,11 @@ int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = std::getenv("MMPL_B200_NO_PDL") == nullptr;
+  return on;
 }
 
 bool device_is_sm100() {

@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 namespace mmpl {
 
@@ -39,6 +40,27 @@ void set_error(const char* fmt, ...);
 const CUtensorMap* get_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                                        uint32_t box_rows);
 void clear_tensor_map_cache();
+
+// A failed launch is picked up by the MMPL_CUDA(cudaGetLastError()) that follows every launch site.
+#define MMPL_CUDA_LAUNCH(expr) (void)(expr)
+
+// Launch with programmatic stream serialization (PDL, see ptx.cuh) unless MMPL_B200_NO_PDL is set in the environment.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Number of SMs on the current device (cached) and sm_100 check.
 int sm_count();

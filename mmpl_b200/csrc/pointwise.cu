@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32)
 ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ldo,
           int S, float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
           int64_t mod_stride, int rows_per_frame) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   constexpr int D = NCH * 256;
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -135,6 +137,8 @@ template <int NCH>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ldo,
                int S, const __nv_bfloat16* __restrict__ w, float eps) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= S) return;
@@ -193,6 +197,8 @@ qk_norm_rope_kv_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
                        const double2* __restrict__ rope_tab, __nv_bfloat16* __restrict__ q_out, int64_t ldq,
                        __nv_bfloat16* __restrict__ k_dst, __nv_bfloat16* __restrict__ v_dst, int64_t ldkv,
                        const RopeKVParams p) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.S) return;
@@ -253,6 +259,8 @@ qk_norm_rope_kv_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
 __global__ void modulation_add_kernel(const __nv_bfloat16* __restrict__ mod, const __nv_bfloat16* __restrict__ src,
                                       int64_t src_fstride, int64_t src_jstride, __nv_bfloat16* __restrict__ out,
                                       int F, int J, int D) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int64_t n = static_cast<int64_t>(F) * J * D;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -268,6 +276,8 @@ __global__ void modulation_add_kernel(const __nv_bfloat16* __restrict__ mod, con
 // ------------------------------------------------------------------------------------------------
 // sinusoidal_embedding_1d (model.py:15-25) in float64, cast to bf16 via float: out[f][0:half]=cos, [half:]=sin
 __global__ void sinusoid_kernel(const double* __restrict__ t, __nv_bfloat16* __restrict__ out, int F, int dim) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F * half) return;
@@ -287,6 +297,8 @@ __global__ void __launch_bounds__(256)
 skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                      const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, int64_t ldo,
                      int M, int N, int K, int silu_in, int silu_out) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -329,6 +341,8 @@ skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __n
 // (the im2col of patch_embedding Conv3d, causal_model.py:812; x is the [F,C,H,W] latent chunk)
 __global__ void patchify_kernel(const __nv_bfloat16* __restrict__ x, int64_t stride_f, int64_t stride_c,
                                 __nv_bfloat16* __restrict__ a, int F, int C, int H, int W) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int gh = H / 2, gw = W / 2;
   const int K = C * 4;
   const int64_t n = static_cast<int64_t>(F) * gh * gw * K;
@@ -351,6 +365,8 @@ __global__ void unpatchify_x0_kernel(const __nv_bfloat16* __restrict__ head, int
                                      const __nv_bfloat16* __restrict__ xt, int64_t xt_stride_f, int64_t xt_stride_c,
                                      const double* __restrict__ sigma, __nv_bfloat16* __restrict__ flow,
                                      __nv_bfloat16* __restrict__ x0, int F, int C, int H, int W) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   const int gh = H / 2, gw = W / 2;
   const int64_t n = static_cast<int64_t>(F) * C * H * W;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -376,6 +392,8 @@ __global__ void unpatchify_x0_kernel(const __nv_bfloat16* __restrict__ head, int
 __global__ void add_noise_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ noise,
                                  const float* __restrict__ sigma, __nv_bfloat16* __restrict__ out,
                                  int64_t per_frame, int64_t n) {
+  pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
+  pdl_launch_dependents();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float s = sigma[i / per_frame];
@@ -410,10 +428,10 @@ int ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D
   MMPL_CHECK(shift && scale && rows_per_frame > 0 && mod_stride % 8 == 0, MMPL_ERR_ARG, "ln_modulate: bad modulation args");
   MMPL_CHECK((S + rows_per_frame - 1) / rows_per_frame <= kMaxFrames, MMPL_ERR_SHAPE, "ln_modulate: too many frames");
   const int grid = (S + kRowsPerBlock - 1) / kRowsPerBlock;
-  MMPL_DISPATCH_NCH(D, (ln_kernel<NCH, false><<<grid, kRowsPerBlock * 32, 0, st>>>(
+  MMPL_DISPATCH_NCH(D, (MMPL_CUDA_LAUNCH(launch_kernel(ln_kernel<NCH, false>, grid, kRowsPerBlock * 32, 0, st, 
                            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, S, eps,
                            static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale),
-                           mod_stride, rows_per_frame)));
+                           mod_stride, rows_per_frame))));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -423,9 +441,9 @@ int ln_affine(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, 
   MMPL_CHECK(S > 0 && D % 256 == 0 && ldx % 8 == 0 && ldo % 8 == 0, MMPL_ERR_SHAPE, "ln_affine: bad shape S=%d D=%d", S, D);
   MMPL_CHECK(weight && bias, MMPL_ERR_ARG, "ln_affine: weight and bias required");
   const int grid = (S + kRowsPerBlock - 1) / kRowsPerBlock;
-  MMPL_DISPATCH_NCH(D, (ln_kernel<NCH, true><<<grid, kRowsPerBlock * 32, 0, st>>>(
+  MMPL_DISPATCH_NCH(D, (MMPL_CUDA_LAUNCH(launch_kernel(ln_kernel<NCH, true>, grid, kRowsPerBlock * 32, 0, st, 
                            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, S, eps,
-                           static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(weight), 0, 1 << 30)));
+                           static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(weight), 0, 1 << 30))));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -434,9 +452,9 @@ int rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, co
             cudaStream_t st) {
   MMPL_CHECK(S > 0 && D % 256 == 0 && ldx % 8 == 0 && ldo % 8 == 0, MMPL_ERR_SHAPE, "rmsnorm: bad shape S=%d D=%d", S, D);
   const int grid = (S + kRowsPerBlock - 1) / kRowsPerBlock;
-  MMPL_DISPATCH_NCH(D, (rmsnorm_kernel<NCH><<<grid, kRowsPerBlock * 32, 0, st>>>(
+  MMPL_DISPATCH_NCH(D, (MMPL_CUDA_LAUNCH(launch_kernel(rmsnorm_kernel<NCH>, grid, kRowsPerBlock * 32, 0, st, 
                            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, S,
-                           static_cast<const __nv_bfloat16*>(weight), eps)));
+                           static_cast<const __nv_bfloat16*>(weight), eps))));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -459,12 +477,12 @@ int qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, int64_
     p.kv_row[f] = kv_row[f];
   }
   const int grid = (S + kRowsPerBlock - 1) / kRowsPerBlock;
-  MMPL_DISPATCH_NCH(D, (qk_norm_rope_kv_kernel<NCH><<<grid, kRowsPerBlock * 32, 0, st>>>(
+  MMPL_DISPATCH_NCH(D, (MMPL_CUDA_LAUNCH(launch_kernel(qk_norm_rope_kv_kernel<NCH>, grid, kRowsPerBlock * 32, 0, st, 
                            static_cast<const __nv_bfloat16*>(q_in), static_cast<const __nv_bfloat16*>(k_in),
                            static_cast<const __nv_bfloat16*>(v_in), ld_in, static_cast<const __nv_bfloat16*>(wq),
                            static_cast<const __nv_bfloat16*>(wk), static_cast<const double2*>(rope_table),
                            static_cast<__nv_bfloat16*>(q_out), ldq, static_cast<__nv_bfloat16*>(k_dst),
-                           static_cast<__nv_bfloat16*>(v_dst), ldkv, p)));
+                           static_cast<__nv_bfloat16*>(v_dst), ldkv, p))));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -473,9 +491,9 @@ int modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_
                    int J, int D, cudaStream_t st) {
   MMPL_CHECK(F > 0 && J > 0 && D > 0, MMPL_ERR_SHAPE, "modulation_add: bad shape");
   const int64_t n = static_cast<int64_t>(F) * J * D;
-  modulation_add_kernel<<<grid_for(n, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(mod),
+  MMPL_CUDA_LAUNCH(launch_kernel(modulation_add_kernel, grid_for(n, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(mod),
                                                           static_cast<const __nv_bfloat16*>(src), src_fstride,
-                                                          src_jstride, static_cast<__nv_bfloat16*>(out), F, J, D);
+                                                          src_jstride, static_cast<__nv_bfloat16*>(out), F, J, D));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -483,7 +501,7 @@ int modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_
 int sinusoid_embedding(const double* t, void* out, int F, int dim, cudaStream_t st) {
   MMPL_CHECK(F > 0 && dim > 0 && dim % 2 == 0, MMPL_ERR_SHAPE, "sinusoid_embedding: bad shape");
   const int n = F * dim / 2;
-  sinusoid_kernel<<<(n + 127) / 128, 128, 0, st>>>(t, static_cast<__nv_bfloat16*>(out), F, dim);
+  MMPL_CUDA_LAUNCH(launch_kernel(sinusoid_kernel, (n + 127) / 128, 128, 0, st, t, static_cast<__nv_bfloat16*>(out), F, dim));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -494,13 +512,13 @@ int skinny_linear(const void* x, int64_t ldx, const void* w, const void* b, void
              "skinny_linear: bad shape M=%d N=%d K=%d", M, N, K);
   const int grid = (N + 7) / 8;
   if (M <= 4)
-    skinny_linear_kernel<4><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+    MMPL_CUDA_LAUNCH(launch_kernel(skinny_linear_kernel<4>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(x), ldx,
                                                   static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(b),
-                                                  static_cast<__nv_bfloat16*>(out), ldo, M, N, K, silu_in, silu_out);
+                                                  static_cast<__nv_bfloat16*>(out), ldo, M, N, K, silu_in, silu_out));
   else
-    skinny_linear_kernel<8><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+    MMPL_CUDA_LAUNCH(launch_kernel(skinny_linear_kernel<8>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(x), ldx,
                                                   static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(b),
-                                                  static_cast<__nv_bfloat16*>(out), ldo, M, N, K, silu_in, silu_out);
+                                                  static_cast<__nv_bfloat16*>(out), ldo, M, N, K, silu_in, silu_out));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -508,8 +526,8 @@ int skinny_linear(const void* x, int64_t ldx, const void* w, const void* b, void
 int patchify(const void* x, int64_t stride_f, int64_t stride_c, void* a, int F, int C, int H, int W, cudaStream_t st) {
   MMPL_CHECK(F > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, MMPL_ERR_SHAPE, "patchify: bad shape");
   const int64_t n = static_cast<int64_t>(F) * C * H * W;
-  patchify_kernel<<<grid_for(n, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), stride_f, stride_c,
-                                                    static_cast<__nv_bfloat16*>(a), F, C, H, W);
+  MMPL_CUDA_LAUNCH(launch_kernel(patchify_kernel, grid_for(n, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(x), stride_f, stride_c,
+                                                    static_cast<__nv_bfloat16*>(a), F, C, H, W));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -519,9 +537,9 @@ int unpatchify_x0(const void* head, int64_t ldh, const void* xt, int64_t xt_stri
   MMPL_CHECK(F > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, MMPL_ERR_SHAPE, "unpatchify_x0: bad shape");
   MMPL_CHECK(x0 == nullptr || (xt && sigma), MMPL_ERR_ARG, "unpatchify_x0: x0 output needs xt and sigma");
   const int64_t n = static_cast<int64_t>(F) * C * H * W;
-  unpatchify_x0_kernel<<<grid_for(n, 256), 256, 0, st>>>(
+  MMPL_CUDA_LAUNCH(launch_kernel(unpatchify_x0_kernel, grid_for(n, 256), 256, 0, st, 
       static_cast<const __nv_bfloat16*>(head), ldh, static_cast<const __nv_bfloat16*>(xt), xt_stride_f, xt_stride_c,
-      sigma, static_cast<__nv_bfloat16*>(flow), static_cast<__nv_bfloat16*>(x0), F, C, H, W);
+      sigma, static_cast<__nv_bfloat16*>(flow), static_cast<__nv_bfloat16*>(x0), F, C, H, W));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }
@@ -530,9 +548,9 @@ int add_noise(const void* x0, const void* noise, const float* sigma, void* out, 
               cudaStream_t st) {
   MMPL_CHECK(n_frames > 0 && per_frame > 0, MMPL_ERR_SHAPE, "add_noise: bad shape");
   const int64_t n = per_frame * n_frames;
-  add_noise_kernel<<<grid_for(n, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x0),
+  MMPL_CUDA_LAUNCH(launch_kernel(add_noise_kernel, grid_for(n, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(x0),
                                                      static_cast<const __nv_bfloat16*>(noise), sigma,
-                                                     static_cast<__nv_bfloat16*>(out), per_frame, n);
+                                                     static_cast<__nv_bfloat16*>(out), per_frame, n));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }

@@ -59,6 +59,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// "_elect" wrappers: called by EVERY lane of a converged warp, one elected lane issues the instruction.
+// The single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) take their operands from uniform registers. When
+// the issuing code sits inside `if (lane == 0)`, ptxas must assume divergent operand values and wraps every such
+// instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~15 instructions, ~100 clk per tcgen05.mma: slower than
+// the MMA itself). Computing the operands warp-uniformly and predicating only the instruction keeps them in uniform
+// registers.
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+
 // --------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -73,6 +89,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
+      "r"(c1), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_elect(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                  int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
       "r"(c1), "l"(policy)
       : "memory");
@@ -108,6 +136,17 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
       "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2cta_elect(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                       int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu),
+      "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)
@@ -124,6 +163,28 @@ __device__ __forceinline__ void tc_commit_2cta(uint64_t* bar, uint16_t cta_mask)
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// Descriptors are passed as (low word, high word): only the low word (start address) changes between MMAs, so the
+// high word stays a constant and one 32-bit add per operand is all the per-MMA address arithmetic.
+__device__ __forceinline__ void umma_ss_2cta_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; issued by the leader CTA.
@@ -162,6 +223,15 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers (thread = lane = accumulator row).
@@ -217,6 +287,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// The address-independent part of the descriptor (start address field = 0); smem addresses are < 256 KB, so adding
+// (address >> 4) to the low word cannot carry out of the 14-bit field.
+__host__ __device__ constexpr uint64_t make_smem_desc_sw128_const(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) | (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+__host__ __device__ constexpr uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
@@ -244,6 +323,30 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_ss_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -290,6 +393,15 @@ __device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& out_lo, float& 
   out_lo = __uint_as_float(__float_as_uint(plo) + (__float_as_uint(tlo) << 23));
   out_hi = __uint_as_float(__float_as_uint(phi) + (__float_as_uint(thi) << 23));
 }
+
+// --------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the forward is launched with programmatic stream serialization (host_util.h: launch_kernel): its
+// CTAs may become resident and run their prologue (barrier init, TMEM allocation, descriptor prefetch) while the
+// previous kernel in the stream is still draining. pdl_wait() blocks until that kernel has completed and its writes
+// are visible, so it must precede the first global-memory access; pdl_launch_dependents() then lets the NEXT kernel
+// start its own prologue. Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------- misc
 // 32-byte (one full sector) global store / load; address must be 32-byte aligned.
