@@ -35,10 +35,7 @@
 #define MMPL_ATTN_PROD 1
 #endif
 #ifndef MMPL_ATTN_HALVES
-#define MMPL_ATTN_HALVES 0
-#endif
-#ifndef MMPL_ATTN_STALE_MAX
-#define MMPL_ATTN_STALE_MAX 0
+#define MMPL_ATTN_HALVES 1
 #endif
 
 #ifndef MMPL_ATTN_TIMING
@@ -59,28 +56,28 @@ __device__ long long g_attn_dbg[32];
 namespace mmpl {
 namespace MMPL_ATTN_NS {
 
-// 12 warps: warpgroup 0 = control (warp 0 TMA producer, warp 1 MMA issuer, 2 idle), warpgroups 1 and 2 = softmax of
-// query tile 0 / 1. setmaxnreg moves registers from the control warpgroup to the softmax warpgroups:
-// 128 x 96 + 256 x 200 = 63488 <= 384 x 168 (the launch allocation; exceeding it deadlocks setmaxnreg.inc). (ptxas bounds the code that follows each setmaxnreg by its value: with 56 registers
-// the control warps spilled their loop state and the MMA issue slowed down by ~25 %.)
+// Warpgroup 0 = control (warp 0 TMA producer, warp 1 MMA issuer, 2 idle); warpgroups 1, 2 = softmax of query tile 0 / 1.
+// setmaxnreg moves registers from the control warpgroup to the softmax warpgroups; the sum must stay within the launch
+// allocation (threads x registers ptxas reports): exceeding it deadlocks setmaxnreg.inc.
+// 12 warps, one thread per query row: 128 x 96 + 256 x 200 = 63488 <= 384 x 168.
 constexpr int kAttnThreads = 384;
-constexpr int kFirstSoftmaxWarp = 4;
+constexpr int kSoftmaxWarpsPerTile = 4;
 #ifndef MMPL_ATTN_CTRL_REGS
 #define MMPL_ATTN_CTRL_REGS 96
 #define MMPL_ATTN_SOFTMAX_REGS 200
 #endif
-constexpr int kAttnThreadsUnused = 320;  // warps 0,1 = TMA, MMA; warps 2-5 / 6-9 = softmax of query tile 0 / 1
+constexpr int kFirstSoftmaxWarp = 4;
 constexpr int kQTile = 128;
 constexpr int kKVTile = 128;
 constexpr int kHD = 128;
 constexpr int kBoxBytes = 128 * 64 * 2;  // one [128 rows][64 bf16] swizzled box = 16 KB
 constexpr int kKVStages = 2;
 constexpr int kAttnSmem = 4 * kBoxBytes /*Q*/ + kKVStages * 2 * kBoxBytes /*K*/ +
-                          kKVStages * 2 * kBoxBytes /*V*/ + 1024 + 256;
+                          kKVStages * 2 * kBoxBytes /*V*/ + 1024 + 256 /*barriers*/;
 constexpr int kMaxSeg = 8;
 constexpr int kUnitRows = 2 * kQTile;
 #ifndef MMPL_ATTN_POLY_NUM
-#define MMPL_ATTN_POLY_NUM 7
+#define MMPL_ATTN_POLY_NUM 4
 #endif
 constexpr int kPolyNum = MMPL_ATTN_POLY_NUM;  // pairs per kPolyDen whose exp2 runs on the FMA/ALU pipes
 constexpr int kPolyDen = 16;
@@ -208,9 +205,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
-        mbar_init(&p_full[2 * i], 4);
-        mbar_init(&p_full[2 * i + 1], 4);
-        mbar_init(&o_empty[i], 4);
+        mbar_init(&p_full[2 * i], kSoftmaxWarpsPerTile);
+        mbar_init(&p_full[2 * i + 1], kSoftmaxWarpsPerTile);
+        mbar_init(&o_empty[i], kSoftmaxWarpsPerTile);
       }
       mbar_init(o_full, 1);
       fence_mbar_init();
@@ -283,8 +280,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // O_q += P_q . V(stage) : 8 k-steps of 16 kv rows; V is MN-major (hd contiguous), the two
       // 64-wide hd halves are 16 KB apart (LBO), 8-row kv groups 1 KB apart (SBO).
       auto issue_pv = [&](int qt, int st, int half, bool first) {
-#pragma unroll
         const uint32_t b0 = desc_lo(kDescV) + ((v_addr + st * 2 * kBoxBytes) >> 4);
+#pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int k = half * 4 + kk;
           umma_ts_elect(tmem_base + 256 + qt * 128, tmem_base + qt * 128 + 8 * k, b0 + k * (2048 >> 4), desc_hi(kDescV),
@@ -383,110 +380,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       float l_run = 0.f;
       TileIter it;
       it.init(p, t0);
-#if MMPL_ATTN_STALE_MAX
-      // One pass over the 128 scores of this row, 32 columns at a time; the tcgen05.ld of chunk c+1 is in flight while
-      // chunk c is processed. kMaxOnly: row maximum only. Otherwise P = 2^(S*scale - m_run) with the running maximum of
-      // the PREVIOUS tiles (the row maximum of this tile is gathered on the side, on the ALU pipe): the exponentials do
-      // not wait for a max pass over the tile. The caller checks afterwards whether the maximum grew by more than the
-      // lazy-rescale threshold and, in that rare case, repeats the pass (S is still intact in TMEM: P is stored later).
-      uint32_t pk[64];
-      float mx_tile, sum_tile;
-      auto pass = [&](auto max_only_tag, int valid) {
-        constexpr bool kMaxOnly = decltype(max_only_tag)::value;
-        float mxk[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        uint64_t sumk[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
-        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
-        const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
-        uint32_t sva[32], svb[32];
-        auto chunk = [&](uint32_t (&sv)[32], int c) {
-          if (valid < kKVTile) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) sv[i] = 0xFF800000u;  // -inf
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            mxk[i & 3] = fmaxf(fmaxf(mxk[i & 3], __uint_as_float(sv[2 * i])), __uint_as_float(sv[2 * i + 1]));
-          if (!kMaxOnly) {
-            // packed fp32x2 FMA for the scaling and the row sum; kPolyNum of every kPolyDen pairs are exponentiated on
-            // the FMA/ALU pipes (exp2_poly_x2) instead of the MUFU (16 ex2/clk/SM against 128 x 128 per tile).
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
-              float p0, p1;
-              if (pair_is_poly(i)) {
-                exp2_poly_x2(x2, p0, p1);
-              } else {
-                float x0, x1;
-                unpack_f32x2(x2, x0, x1);
-                p0 = fast_exp2(x0);
-                p1 = fast_exp2(x1);
-              }
-              sumk[i & 1] = add_f32x2(sumk[i & 1], pack_f32x2(p0, p1));
-              pk[c * 16 + i] = pack_bf16x2(p0, p1);
-            }
-          }
-        };
-        tmem_ld_32x32(t_s, sva);
-        tmem_ld_wait();
-        tmem_ld_32x32(t_s + 32, svb);
-        chunk(sva, 0);
-        tmem_ld_wait();
-        tmem_ld_32x32(t_s + 64, sva);
-        chunk(svb, 1);
-        tmem_ld_wait();
-        tmem_ld_32x32(t_s + 96, svb);
-        chunk(sva, 2);
-        tmem_ld_wait();
-        chunk(svb, 3);
-        mx_tile = fmaxf(fmaxf(mxk[0], mxk[1]), fmaxf(mxk[2], mxk[3]));
-        float s_lo, s_hi;
-        unpack_f32x2(add_f32x2(sumk[0], sumk[1]), s_lo, s_hi);
-        sum_tile = s_lo + s_hi;
-      };
-      for (int jj = 0; jj < n; ++jj, it.next(p)) {
-        const int valid = it.valid();
-        TSTAMP(ts0);
-        mbar_wait(&s_full[qt], (g + jj) & 1);
-        tc_fence_after();
-        TSTAMP(ts1);
-        if (jj == 0) {  // no running maximum yet: take it from this tile
-          pass(std::true_type{}, valid);
-          m_run = mx_tile * p.scale_log2;
-        }
-        for (;;) {
-          pass(std::false_type{}, valid);
-          const float m_new = fmaxf(m_run, mx_tile * p.scale_log2);
-          const bool grow = m_new > m_run + 8.0f;
-          if (!__any_sync(0xffffffffu, grow)) break;
-          // the maximum grew by more than 2^8 somewhere in this warp: rescale l and O, then redo the tile
-          const float alpha = fast_exp2(m_run - m_new);
-          l_run *= alpha;
-          m_run = m_new;
-          if (jj > 0) {
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[32];
-              tmem_ld_32x32(t_o + c * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x32(t_o + c * 32, o);
-            }
-          }
-        }
-        TSTAMP(ts2);
-        tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-        tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * qt + 1]);
-        l_run += sum_tile;
-        TSTAMP(ts3);
-        TACC(0, ts1 - ts0); TACC(1, ts2 - ts1); TACC(2, ts3 - ts2); TACC(3, 1);
-      }
-#else
       for (int jj = 0; jj < n; ++jj, it.next(p)) {
         const int valid = it.valid();
         TSTAMP(ts0);
@@ -570,7 +463,6 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         TSTAMP(ts3);
         TACC(0, ts1 - ts0); TACC(1, ts2 - ts1); TACC(2, ts3 - ts2); TACC(3, 1);
       }
-#endif
       // piece epilogue
       mbar_wait(o_full, piece & 1);
       tc_fence_after();
