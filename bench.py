@@ -275,14 +275,23 @@ def run_ours(args):
     # one extra instrumented step: time share per kernel category (not part of any reported throughput)
     _lib.check(lib.mmpl_profile_enable(ctx, 0xF))
     _lib.check(lib.mmpl_profile_read(ctx, ms_arr, work_arr, n_arr, 1))
+    s_ms, s_work, s_n = (C.c_double * 14)(), (C.c_double * 14)(), (C.c_int64 * 14)()
+    _lib.check(lib.mmpl_profile_read_sites(ctx, s_ms, s_work, s_n, 1))
     ms_prof = timed(step_resident, 1)
     _lib.check(lib.mmpl_profile_read(ctx, ms_arr, work_arr, n_arr, 1))
+    _lib.check(lib.mmpl_profile_read_sites(ctx, s_ms, s_work, s_n, 1))
     _lib.check(lib.mmpl_profile_enable(ctx, 0))
     cats = ["self_attn", "cross_attn", "gemm", "pointwise"]
     breakdown = {c: {"ms": round(ms_arr[i], 3), "launches": int(n_arr[i]),
                      ("tflops" if i < 3 else "gbs"): round(work_arr[i] / max(ms_arr[i], 1e-9) / (1e9 if i < 3 else 1e6), 1)}
                  for i, c in enumerate(cats)}
     breakdown["step_ms_instrumented"] = round(ms_prof, 3)
+    # the same spans by call site inside the block: [ms per step, launches, TFLOP/s or GB/s]
+    site_names = ["self_attn", "cross_attn", "gemm_qkv", "gemm_o", "gemm_cross_q", "gemm_cross_o", "gemm_ffn0", "gemm_ffn2",
+                  "ln_modulate", "ln_affine", "qk_norm_rope_kv", "rmsnorm", "modulation_add", "other"]
+    breakdown["sites"] = {nm: [round(s_ms[i], 3), int(s_n[i]),
+                               round(s_work[i] / max(s_ms[i], 1e-9) / (1e9 if i < 8 else 1e6), 1)]
+                          for i, nm in enumerate(site_names)}
 
     if rank != 0:
         if world > 1:

@@ -68,6 +68,10 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
 
 /* Tuning / test hook: force the number of KV chunks each attention unit is split into (0 = cost model). */
 int mmpl_attn_set_split(int split);
+/* Tuning / test hook: stream-K tail schedule of the cta_group::2 GEMM: 0 = never (default; slower on B200 at the
+ * cfg2 shapes, see gemm_tcgen05.cu), -1 = automatic (when whole 256x256 tiles would leave more than 4 % of the last
+ * wave empty), 1 = whenever tiles % pairs != 0. */
+int mmpl_gemm_set_streamk(int mode);
 
 /* bf16(bf16(bf16(LayerNorm(x)) * bf16(1 + scale_f)) + shift_f); shift/scale are [frames][mod_stride]
  * (causal_model.py:305,318; WanLayerNorm model.py:89-99). D in {256,512,1536,5120}. */
@@ -147,6 +151,14 @@ int64_t mmpl_total_launches(int reset);
 enum { MMPL_PROF_SELF_ATTN = 0, MMPL_PROF_CROSS_ATTN = 1, MMPL_PROF_GEMM = 2, MMPL_PROF_POINTWISE = 3, MMPL_PROF_NCAT = 4 };
 int mmpl_profile_enable(mmpl_ctx* ctx, int category_mask);
 int mmpl_profile_read(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches, int reset);
+/* The same spans split by call site inside CausalWanAttentionBlock.forward (causal_model.py:274-326): arrays of
+ * MMPL_SITE_COUNT entries. Diagnostic only (bench.py "breakdown.sites", tools/). */
+enum {
+  MMPL_SITE_SELF_ATTN = 0, MMPL_SITE_CROSS_ATTN = 1, MMPL_SITE_GEMM_QKV = 2, MMPL_SITE_GEMM_O = 3, MMPL_SITE_GEMM_CQ = 4,
+  MMPL_SITE_GEMM_CO = 5, MMPL_SITE_GEMM_FFN0 = 6, MMPL_SITE_GEMM_FFN2 = 7, MMPL_SITE_LN_MOD = 8, MMPL_SITE_LN_AFFINE = 9,
+  MMPL_SITE_ROPE_KV = 10, MMPL_SITE_RMSNORM = 11, MMPL_SITE_MODADD = 12, MMPL_SITE_OTHER = 13, MMPL_SITE_COUNT = 14
+};
+int mmpl_profile_read_sites(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches, int reset);
 
 typedef struct {
   /* latent chunk [n_frames][in_dim][lat_h][lat_w] (strides in elements) */

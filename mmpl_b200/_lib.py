@@ -48,6 +48,7 @@ SIGNATURES = {
                                c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mmpl_flash_attn": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_int64, c_float, c_void_p]),
+    "mmpl_gemm_set_streamk": (c_int, [c_int]),
     "mmpl_attn_set_split": (c_int, [c_int]),
     "mmpl_ln_modulate": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_int64, c_int, c_void_p]),
@@ -73,6 +74,7 @@ SIGNATURES = {
     "mmpl_total_launches": (c_int64, [c_int]),
     "mmpl_profile_enable": (c_int, [c_void_p, c_int]),
     "mmpl_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),
+    "mmpl_profile_read_sites": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),
 }
 
 

@@ -84,12 +84,21 @@ struct mmpl_ctx {
   double prof_ms[MMPL_PROF_NCAT] = {0, 0, 0, 0};
   int64_t prof_launches[MMPL_PROF_NCAT] = {0, 0, 0, 0};
   double prof_work[MMPL_PROF_NCAT] = {0, 0, 0, 0};  // algorithmic FLOPs (cat 0-2) or bytes (cat 3)
+  // the same spans by call site inside the block (MMPL_SITE_*): which Linear / norm the time belongs to
+  int cur_site = MMPL_SITE_OTHER;
+  double site_ms[MMPL_SITE_COUNT] = {};
+  double site_work[MMPL_SITE_COUNT] = {};
+  int64_t site_launches[MMPL_SITE_COUNT] = {};
   // workspace (device)
   char* ws = nullptr;
   size_t ws_bytes = 0;
   void *x = nullptr, *xm = nullptr, *qkv = nullptr, *attn = nullptr, *h = nullptr, *patch = nullptr, *hout = nullptr;
   void *sinus = nullptr, *t1 = nullptr, *e = nullptr, *e0 = nullptr, *emod = nullptr, *ehead = nullptr;
   void *ctx_h = nullptr, *ctx_e = nullptr, *tail_k = nullptr, *tail_v = nullptr;
+  // device table of the blocks' `modulation` parameters (re-uploaded after a bind) for modulation_add_layers
+  void* mod_table = nullptr;
+  std::vector<const void*> mod_table_host;
+  bool mod_table_dirty = true;
 };
 
 static int64_t g_total_launches = 0;
@@ -119,6 +128,11 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   MMPL_CHECK(q && k0 && v0 && out && seg_start && seg_rows, MMPL_ERR_ARG, "flash_attn: null argument");
   COUNTED(flash_attn_bf16(q, ldq, Lq, H, k0, v0, ldkv0, rows0, k1, v1, ldkv1, rows1, nseg, seg_start, seg_rows,
                          seg_src, out, ldo, softmax_scale, static_cast<cudaStream_t>(stream)));
+}
+
+int mmpl_gemm_set_streamk(int mode) {
+  gemm_set_streamk(mode);
+  return MMPL_OK;
 }
 
 int mmpl_attn_set_split(int split) {
@@ -198,9 +212,10 @@ int mmpl_ctx_create(const mmpl_model_config* cfg, mmpl_ctx** out) {
       al(S * pk * 2),          // patch
       al(S * po * 2),          // hout
       al(32 * cfg->freq_dim * 2), al(32 * D * 2), al(32 * D * 2), al(32 * 6 * D * 2),  // sinus t1 e e0
-      al(32 * 6 * D * 2), al(32 * 2 * D * 2),                                          // emod ehead
+      al(static_cast<size_t>(cfg->num_layers) * 32 * 6 * D * 2), al(32 * 2 * D * 2),   // emod (all blocks) ehead
       al(T * D * 2), al(T * D * 2),                                                    // ctx_h ctx_e
       al(S * D * 2), al(S * D * 2),                                                    // tail_k tail_v
+      al(static_cast<size_t>(cfg->num_layers) * sizeof(void*)),                        // mod_table
   };
   size_t total = 0;
   for (size_t s : sizes) total += s;
@@ -212,7 +227,7 @@ int mmpl_ctx_create(const mmpl_model_config* cfg, mmpl_ctx** out) {
   }
   c->ws_bytes = total;
   void** slots[] = {&c->x, &c->xm, &c->qkv, &c->attn, &c->h, &c->patch, &c->hout, &c->sinus, &c->t1,
-                    &c->e, &c->e0, &c->emod, &c->ehead, &c->ctx_h, &c->ctx_e, &c->tail_k, &c->tail_v};
+                    &c->e, &c->e0, &c->emod, &c->ehead, &c->ctx_h, &c->ctx_e, &c->tail_k, &c->tail_v, &c->mod_table};
   size_t off = 0;
   for (size_t i = 0; i < sizeof(sizes) / sizeof(sizes[0]); ++i) {
     *slots[i] = c->ws + off;
@@ -243,6 +258,7 @@ int mmpl_bind_weight(mmpl_ctx* ctx, const char* name, const void* ptr, int64_t n
         MMPL_CHECK(expect[f.kind] < 0 || expect[f.kind] == numel, MMPL_ERR_SHAPE, "bind_weight: %s has %lld elements, expected %lld",
                    name, (long long)numel, (long long)expect[f.kind]);
         *reinterpret_cast<const void**>(reinterpret_cast<char*>(&ctx->layers[li]) + f.offset) = ptr;
+        ctx->mod_table_dirty = true;
         return MMPL_OK;
       }
     }
@@ -293,10 +309,13 @@ static cudaEvent_t prof_event(mmpl_ctx* ctx) {
     if (_prof) {                                                              \
       const size_t _i1 = ctx->ev_used;                                        \
       cudaEventRecord(prof_event(ctx), st);                                   \
-      ctx->ev_spans.push_back({(cat), {_i0, _i1}});                           \
+      ctx->ev_spans.push_back({(cat) | (ctx->cur_site << 8), {_i0, _i1}});    \
       ctx->prof_work[(cat)] += (work);                                        \
       ++ctx->prof_launches[(cat)];                                            \
+      ctx->site_work[ctx->cur_site] += (work);                                \
+      ++ctx->site_launches[ctx->cur_site];                                    \
     }                                                                         \
+    ctx->cur_site = MMPL_SITE_OTHER;                                          \
     ++ctx->launches;                                                          \
     ++g_total_launches;                                                       \
   } while (0)
@@ -314,7 +333,8 @@ int mmpl_profile_read(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches
     MMPL_CUDA(cudaEventSynchronize(b));
     float t = 0.f;
     MMPL_CUDA(cudaEventElapsedTime(&t, a, b));
-    ctx->prof_ms[sp.first] += t;
+    ctx->prof_ms[sp.first & 0xFF] += t;
+    ctx->site_ms[sp.first >> 8] += t;
   }
   ctx->ev_spans.clear();
   ctx->ev_used = 0;
@@ -323,6 +343,17 @@ int mmpl_profile_read(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches
     work[i] = ctx->prof_work[i];
     launches[i] = ctx->prof_launches[i];
     if (reset) { ctx->prof_ms[i] = 0; ctx->prof_work[i] = 0; ctx->prof_launches[i] = 0; }
+  }
+  return MMPL_OK;
+}
+
+int mmpl_profile_read_sites(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches, int reset) {
+  MMPL_CHECK(ctx && ms && work && launches, MMPL_ERR_ARG, "profile_read_sites: null argument");
+  for (int i = 0; i < MMPL_SITE_COUNT; ++i) {
+    ms[i] = ctx->site_ms[i];
+    work[i] = ctx->site_work[i];
+    launches[i] = ctx->site_launches[i];
+    if (reset) { ctx->site_ms[i] = 0; ctx->site_work[i] = 0; ctx->site_launches[i] = 0; }
   }
   return MMPL_OK;
 }
@@ -368,7 +399,6 @@ int mmpl_forward(mmpl_ctx* ctx, const mmpl_forward_args* a, void* stream_v) {
   bf* attn = static_cast<bf*>(ctx->attn);
   bf* hbuf = static_cast<bf*>(ctx->h);
   bf* e0 = static_cast<bf*>(ctx->e0);
-  bf* emod = static_cast<bf*>(ctx->emod);
   bf* ehead = static_cast<bf*>(ctx->ehead);
   const GlobalWeights& g = ctx->g;
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)
@@ -405,36 +435,58 @@ int mmpl_forward(mmpl_ctx* ctx, const mmpl_forward_args* a, void* stream_v) {
   double lk_self = 0;
   for (int i = 0; i < nseg; ++i) lk_self += seg_rows[i];
 
+  // e = modulation + e0 of every block (causal_model.py:300), one launch: e0 is fixed for the whole forward
+  if (ctx->mod_table_dirty) {
+    ctx->mod_table_host.resize(L);
+    for (int l = 0; l < L; ++l) ctx->mod_table_host[l] = ctx->layers[l].modulation;
+    MMPL_CUDA(cudaMemcpyAsync(ctx->mod_table, ctx->mod_table_host.data(), L * sizeof(void*), cudaMemcpyHostToDevice, st));
+    ctx->mod_table_dirty = false;
+  }
+  ctx->cur_site = MMPL_SITE_MODADD;
+  RUN(3, 0.0, modulation_add_layers(static_cast<const void* const*>(ctx->mod_table), e0, ctx->emod, L, F, D, st));
+
   for (int l = 0; l < L; ++l) {
     const LayerWeights& w = ctx->layers[l];
     bf* kc = static_cast<bf*>(a->kv_k[l]);
     bf* vc = static_cast<bf*>(a->kv_v[l]);
-    // e = modulation + e0 (causal_model.py:300)
-    RUN(3, 0.0, modulation_add(w.modulation, e0, 6 * D, D, emod, F, 6, D, st));
+    bf* emod = static_cast<bf*>(ctx->emod) + static_cast<size_t>(l) * F * 6 * D;
     // self-attention (causal_model.py:304-310, 86-231)
+    ctx->cur_site = MMPL_SITE_LN_MOD;
     RUN(3, 4.0 * S * D, ln_modulate(x, D, xm, D, S, D, c.eps, emod + 0 * D, emod + 1 * D, 6 * D, fs, st));
+    ctx->cur_site = MMPL_SITE_GEMM_QKV;
     RUN(2, 6.0 * S * D * D, gemm_bf16(xm, D, w.qkv_w, D, w.qkv_b, qkv, 3 * D, S, 3 * D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+    ctx->cur_site = MMPL_SITE_ROPE_KV;
     RUN(3, 12.0 * S * D, qk_norm_rope_kv(qkv, qkv + D, qkv + 2 * D, 3 * D, w.norm_q, w.norm_k, ctx->rope_table, qkv, 3 * D,
                         a->kv_to_tail ? ctx->tail_k : kc, a->kv_to_tail ? ctx->tail_v : vc, D, S, D, gh, gw, F,
                         a->frame_pos, a->kv_row, c.eps, st));
+    ctx->cur_site = MMPL_SITE_SELF_ATTN;
     RUN(0, 4.0 * S * lk_self * D, flash_attn_bf16(qkv, 3 * D, S, H, kc, vc, D, static_cast<int>(a->cache_rows), ctx->tail_k, ctx->tail_v, D, S,
                         nseg, seg_start, seg_rows, seg_src, attn, D, scale, st));
+    ctx->cur_site = MMPL_SITE_GEMM_O;
     RUN(2, 2.0 * S * D * D, gemm_bf16(attn, D, w.o_w, D, w.o_b, x, D, S, D, D, MMPL_EPI_BIAS_GATE_RES, x, D, emod + 2 * D, 6 * D, fs, 0, st));
     // cross-attention (causal_model.py:314; model.py:159-194)
+    ctx->cur_site = MMPL_SITE_LN_AFFINE;
     RUN(3, 4.0 * S * D, ln_affine(x, D, xm, D, S, D, c.eps, w.norm3_w, w.norm3_b, st));
+    ctx->cur_site = MMPL_SITE_GEMM_CQ;
     RUN(2, 2.0 * S * D * D, gemm_bf16(xm, D, w.cq_w, D, w.cq_b, qkv, D, S, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
+    ctx->cur_site = MMPL_SITE_RMSNORM;
     RUN(3, 4.0 * S * D, rmsnorm(qkv, D, qkv, D, S, D, w.cnorm_q, c.eps, st));
     if (!a->cross_init) {
       RUN(2, 2.0 * T * D * D, gemm_bf16(ctx->ctx_e, D, w.ck_w, D, w.ck_b, a->cross_k[l], D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
       RUN(3, 4.0 * T * D, rmsnorm(a->cross_k[l], D, a->cross_k[l], D, T, D, w.cnorm_k, c.eps, st));
       RUN(2, 2.0 * T * D * D, gemm_bf16(ctx->ctx_e, D, w.cv_w, D, w.cv_b, a->cross_v[l], D, T, D, D, MMPL_EPI_BIAS, nullptr, 0, nullptr, 0, 0, 0, st));
     }
+    ctx->cur_site = MMPL_SITE_CROSS_ATTN;
     RUN(1, 4.0 * S * T * D, flash_attn_bf16(qkv, D, S, H, a->cross_k[l], a->cross_v[l], D, T, nullptr, nullptr, 0, 0, 1, &cross_start,
                         &cross_rows, nullptr, attn, D, scale, st));
+    ctx->cur_site = MMPL_SITE_GEMM_CO;
     RUN(2, 2.0 * S * D * D, gemm_bf16(attn, D, w.co_w, D, w.co_b, x, D, S, D, D, MMPL_EPI_BIAS_RES, x, D, nullptr, 0, 0, 0, st));
     // feed-forward (causal_model.py:316-322)
+    ctx->cur_site = MMPL_SITE_LN_MOD;
     RUN(3, 4.0 * S * D, ln_modulate(x, D, xm, D, S, D, c.eps, emod + 3 * D, emod + 4 * D, 6 * D, fs, st));
+    ctx->cur_site = MMPL_SITE_GEMM_FFN0;
     RUN(2, 2.0 * S * D * Fd, gemm_bf16(xm, D, w.ffn0_w, D, w.ffn0_b, hbuf, Fd, S, Fd, D, MMPL_EPI_BIAS_GELU, nullptr, 0, nullptr, 0, 0, 0, st));
+    ctx->cur_site = MMPL_SITE_GEMM_FFN2;
     RUN(2, 2.0 * S * D * Fd, gemm_bf16(hbuf, Fd, w.ffn2_w, Fd, w.ffn2_b, x, D, S, D, Fd, MMPL_EPI_BIAS_GATE_RES, x, D, emod + 5 * D, 6 * D, fs, 0, st));
   }
 

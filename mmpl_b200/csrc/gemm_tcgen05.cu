@@ -14,6 +14,8 @@
 // left half of the tile's columns, warps 6-9 the right half: two warps per scheduler hide each other's latencies).
 // A/W tiles are [128|BN rows] x [64 k] bf16 boxes in 128B-swizzled smem; the 128 x BN fp32
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cstdlib>
+
 #include "host_util.h"
 #include "mmpl_b200.h"
 #include "ptx.cuh"
@@ -36,6 +38,12 @@ struct GemmParams {
   int64_t gate_stride;
   int rows_per_frame;
   int tiles_m, tiles_n;
+  // stream-K part of the pair kernel's schedule (see PairSched): tiles [0, tiles_dp) are whole-tile work items, the
+  // k blocks of the remaining tiles are dealt out evenly
+  int tiles_dp;
+  int group_m;         // tile order of the pair kernel: groups of group_m tile rows, row-fastest inside a group
+  float* sk_part;      // [pairs][2 CTAs][128 rows][256 columns] fp32 partial accumulators
+  uint32_t* sk_flags;  // [pairs][2 CTAs]: 1 = the partial of this CTA's head segment is in sk_part
 };
 
 template <int BN>
@@ -60,9 +68,12 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 
 // Epilogue of one accumulator row: `taddr` addresses this warp's 32 TMEM lanes at the tile's first column; the
 // thread owns output row `row`, columns [col_base, col_base + BN). Rounds to bf16 where the reference does.
+// `part` (stream-K owner segments only): `nparts` fp32 partial accumulator rows of this thread's row, `part_stride`
+// floats apart, written by other CTAs; they are added to the TMEM accumulator before the epilogue arithmetic.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int col_base, int c_begin,
-                                              int c_end) {
+                                              int c_end, const float* part = nullptr, int nparts = 0,
+                                              int64_t part_stride = 0) {
   constexpr bool kHasRes = (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES);
   const bool row_ok = row < p.M;
   const __nv_bfloat16* gate_row = nullptr;
@@ -112,6 +123,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     if (kHasRes && c + 1 < c_end) load_res(c + 1, res_next);
     tmem_ld_wait();
     const int col0 = col_base + c * 32;
+    if (row_ok) {
+      for (int i = 0; i < nparts; ++i) {
+        const float4* src = reinterpret_cast<const float4*>(part + i * part_stride + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = __ldcg(src + j);  // L2: written by another SM during this launch
+          acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+          acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+          acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+          acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+        }
+      }
+    }
     if (row_ok && col0 < p.N) {
 #pragma unroll
       for (int g2 = 0; g2 < 2; ++g2) {
@@ -287,6 +311,86 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// Work list of one CTA pair in the cta_group::2 kernel. Whole tiles alone leave the last wave partly empty (cfg2:
+// M = 4680, N = 1536 is 19 x 6 = 114 tiles of 256 x 256 on 74 pairs, 1.54 waves that take 2), so the schedule is
+// "stream-K" for the tail: tiles [0, tiles_dp) (a multiple of the pair count) are dealt out whole, round-robin; the
+// k blocks of the other tiles form one sequence of (tile, k block) units cut into equal contiguous ranges, one per
+// pair. A range is a head segment (the last k blocks of a tile), whole tiles, and a tail segment (the first k
+// blocks of a tile). The pair that holds a tile's FIRST k blocks owns the tile: it runs that segment last, by
+// which time the pairs holding the rest of the tile -- it is the head segment of their ranges, the first thing
+// they ran -- have left their fp32 partial accumulators in sk_part and raised sk_flags; the owner adds them to its
+// own accumulator in a fixed order (deterministic) and runs the epilogue. Stream-K segments run before the whole
+// tiles, so the hand-over happens mid-kernel behind the main loops.
+struct PairSched {
+  int num_kb, tiles_dp, num_pairs;
+  int sk_pos, sk_hi, dp_t;
+  __device__ __forceinline__ static int range_lo(int pair, int num_pairs, int units) {
+    return static_cast<int>(static_cast<long long>(pair) * units / num_pairs);
+  }
+  __device__ __forceinline__ void init(const GemmParams& p, int pair, int npairs, int nkb) {
+    num_kb = nkb;
+    tiles_dp = p.tiles_dp;
+    num_pairs = npairs;
+    const int units = (p.tiles_m * p.tiles_n - p.tiles_dp) * nkb;
+    sk_pos = range_lo(pair, npairs, units);
+    sk_hi = range_lo(pair + 1, npairs, units);
+    dp_t = pair;
+  }
+  // next segment: tile index and its k-block range [kb0, kb1)
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (sk_pos < sk_hi) {
+      const int t = sk_pos / num_kb;
+      const int end = min(sk_hi, (t + 1) * num_kb);
+      kb0 = sk_pos - t * num_kb;
+      kb1 = end - t * num_kb;
+      tile = tiles_dp + t;
+      sk_pos = end;
+      return true;
+    }
+    if (dp_t < tiles_dp) {
+      tile = dp_t;
+      kb0 = 0;
+      kb1 = num_kb;
+      dp_t += num_pairs;
+      return true;
+    }
+    return false;
+  }
+};
+
+// Tile index -> (tile row, tile column). Tiles that run at the same time (consecutive indices) cover group_m tile rows x
+// (pairs / group_m) tile columns, so one wave re-reads group_m A panels and a few W panels from L2 instead of all
+// of A (at the Wan-14B shapes A alone is 112 MB: row-fastest order over all 43 tile rows streams it from HBM in
+// every wave).
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_blk, int& n_blk) {
+  const int per_group = p.group_m * p.tiles_n;
+  const int g = t / per_group;
+  const int r = t - g * per_group;
+  const int m0 = g * p.group_m;
+  const int gm = min(p.group_m, p.tiles_m - m0);
+  n_blk = r / gm;
+  m_blk = m0 + (r - n_blk * gm);
+}
+
+// Stream-K head segment: this thread's accumulator row (columns [c_begin*32, c_end*32)) -> fp32 workspace row.
+__device__ __forceinline__ void store_partial_row(uint32_t taddr, float* dst, bool row_ok, int c_begin, int c_end) {
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr + c * 32, acc);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[8] = {acc[8 * j], acc[8 * j + 1], acc[8 * j + 2], acc[8 * j + 3],
+                               acc[8 * j + 4], acc[8 * j + 5], acc[8 * j + 6], acc[8 * j + 7]};
+        st_global_v8(dst + c * 32 + 8 * j, w);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void epi_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // warps 2..9
+
 // ------------------------------------------------------------------------------------------------
 // cta_group::2 variant: a pair of CTAs (one cluster of 2, same TPC) computes a 256 x 256 tile with
 // tcgen05.mma.cta_group::2 (M = 256, N = 256). Each CTA loads 128 rows of A and 128 rows (= N/2) of W
@@ -358,12 +462,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ------------------------------------------------ TMA producer (both CTAs, own halves)
     int s = 0;
     uint32_t ph = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m_blk = t % p.tiles_m;
-      const int n_blk = t / p.tiles_m;
+    PairSched sched;
+    sched.init(p, pair, num_pairs, num_kb);
+    int t, kb0, kb1;
+    while (sched.next(t, kb0, kb1)) {
+      int m_blk, n_blk;
+      tile_coords(p, t, m_blk, n_blk);
       const int row_a = m_blk * 256 + static_cast<int>(cta) * kBM;
       const int row_b = n_blk * BN + static_cast<int>(cta) * (BN / 2);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (leader) mbar_arrive_expect_tx_elect(&full_bar[s], 2 * kPairStageBytes);
         tma_load_2d_2cta_elect(smem_a + s * (kPairStageBytes / 2), &map_a, &full_bar[s], kb * kBK, row_a, kEvictNormal);
@@ -378,13 +485,16 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      PairSched sched;
+      sched.init(p, pair, num_pairs, num_kb);
+      int t, kb0, kb1;
+      for (; sched.next(t, kb0, kb1); ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           constexpr uint64_t kDesc0 = make_smem_desc_sw128_const(16, 1024);
@@ -393,9 +503,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
             umma_ss_2cta_elect(tmem_d, a_lo + 2 * k, desc_hi(kDesc0), b_lo + 2 * k, desc_hi(kDesc0), idesc,
-                               (kb | k) != 0 ? 1u : 0u);
+                               ((kb - kb0) | k) != 0 ? 1u : 0u);
           tc_commit_2cta_elect(&empty_bar[s], 0x3);
-          if (kb == num_kb - 1) tc_commit_2cta_elect(&tmem_full[as], 0x3);
+          if (kb == kb1 - 1) tc_commit_2cta_elect(&tmem_full[as], 0x3);
           if (++s == ST) { s = 0; ph ^= 1; }
         }
       }
@@ -404,9 +514,14 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ------------------------------------------------ epilogue (both CTAs, own 128 rows)
     const int lane_base = (warp & 3) * 32;
     int it = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
-      const int m_blk = t % p.tiles_m;
-      const int n_blk = t / p.tiles_m;
+    PairSched sched;
+    sched.init(p, pair, num_pairs, num_kb);
+    const int sk_units = (num_tiles - p.tiles_dp) * num_kb;
+    constexpr int64_t kSlotFloats = 128 * BN;  // one CTA's partial accumulator
+    int t, kb0, kb1;
+    for (; sched.next(t, kb0, kb1); ++it) {
+      int m_blk, n_blk;
+      tile_coords(p, t, m_blk, n_blk);
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aph);
@@ -414,8 +529,42 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int row = m_blk * 256 + static_cast<int>(cta) * kBM + lane_base + lane;
       constexpr int kChunks = BN / 32 / 2;
       const int half = (warp - 2) >> 2;
-      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
-                             half * kChunks, (half + 1) * kChunks);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN;
+      if (kb0 > 0) {
+        // head segment of this pair's stream-K range: leave the partial accumulator for the tile's owner
+        float* dst = p.sk_part + (static_cast<int64_t>(pair) * 2 + cta) * kSlotFloats +
+                     static_cast<int64_t>(lane_base + lane) * BN;
+        store_partial_row(taddr, dst, row < p.M, half * kChunks, (half + 1) * kChunks);
+        __threadfence();
+        epi_group_sync();
+        if (warp == 2 && lane == 0)
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + pair * 2 + cta), "r"(1u) : "memory");
+      } else if (kb1 < num_kb) {
+        // tail segment: this pair owns the tile. The rest of its k blocks are the head segments of the next pairs.
+        const int tile_end = (t - p.tiles_dp + 1) * num_kb;
+        int q_last = pair;
+        for (int covered = sched.sk_hi; covered < tile_end; ) {
+          ++q_last;
+          covered = min(tile_end, PairSched::range_lo(q_last + 1, num_pairs, sk_units));
+        }
+        if (warp == 2 && lane == 0) {
+          for (int q = pair + 1; q <= q_last; ++q) {
+            uint32_t* flag = p.sk_flags + q * 2 + cta;
+            uint32_t v;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            } while (v == 0);
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");  // re-arm for the next launch
+          }
+        }
+        epi_group_sync();
+        const float* part = p.sk_part + (static_cast<int64_t>(pair + 1) * 2 + cta) * kSlotFloats +
+                            static_cast<int64_t>(lane_base + lane) * BN;
+        epilogue_tile<BN, EPI>(p, taddr, row, n_blk * BN, half * kChunks, (half + 1) * kChunks, part, q_last - pair,
+                               2 * kSlotFloats);
+      } else {
+        epilogue_tile<BN, EPI>(p, taddr, row, n_blk * BN, half * kChunks, (half + 1) * kChunks);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
@@ -430,6 +579,32 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
 }
 
+// Stream-K workspace: one fp32 partial-accumulator slot and one flag per CTA (grown on demand; one per process, used
+// by launches on one stream at a time, like the attention workspace). Flags are zero between launches: every raised
+// flag is consumed and cleared by exactly one owner inside the same launch.
+static float* g_sk_part = nullptr;
+static uint32_t* g_sk_flags = nullptr;
+static int g_sk_pairs = 0;
+// 0 never (default), -1 automatic, 1 whenever the tile count is not a multiple of the pair count; MMPL_GEMM_STREAMK sets it.
+// Off by default: measured on B200 (profiles/README.md, round-1 stream-K A/B) the tail schedule loses 9-11 us per
+// launch at the cfg2 shapes. The GEMMs run power-capped at ~1.4-1.65 GHz, so a half-empty last wave is not idle time
+// to recover -- the pairs that are still busy clock higher -- while the owner's fix-up epilogue is exposed.
+static int g_streamk_mode = getenv("MMPL_GEMM_STREAMK") ? atoi(getenv("MMPL_GEMM_STREAMK")) : 0;
+void gemm_set_streamk(int mode) { g_streamk_mode = mode; }
+static int ensure_streamk_workspace(int pairs) {
+  if (pairs <= g_sk_pairs) return MMPL_OK;
+  if (g_sk_part) MMPL_CUDA(cudaFree(g_sk_part));
+  if (g_sk_flags) MMPL_CUDA(cudaFree(g_sk_flags));
+  g_sk_part = nullptr;
+  g_sk_flags = nullptr;
+  g_sk_pairs = 0;
+  MMPL_CUDA(cudaMalloc(&g_sk_part, static_cast<size_t>(pairs) * 2 * 128 * kPairBN * sizeof(float)));
+  MMPL_CUDA(cudaMalloc(&g_sk_flags, static_cast<size_t>(pairs) * 2 * sizeof(uint32_t)));
+  MMPL_CUDA(cudaMemset(g_sk_flags, 0, static_cast<size_t>(pairs) * 2 * sizeof(uint32_t)));
+  g_sk_pairs = pairs;
+  return MMPL_OK;
+}
+
 template <int EPI>
 static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
   auto kern = gemm_bf16_pair_kernel<EPI>;
@@ -442,7 +617,29 @@ static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmPa
   p.tiles_n = (p.N + kPairBN - 1) / kPairBN;
   const int tiles = p.tiles_m * p.tiles_n;
   const int max_pairs = sm_count() / 2;
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  int pairs = tiles < max_pairs ? tiles : max_pairs;
+  // Schedule (PairSched): whole tiles while they fill every pair; stream-K over the k blocks of the rest when whole
+  // tiles would leave more than 4 % of the last wave empty.
+  p.tiles_dp = tiles;
+  {
+    static const int env_gm = getenv("MMPL_GEMM_GROUP_M") ? atoi(getenv("MMPL_GEMM_GROUP_M")) : 0;
+    const bool a_fits_l2 = static_cast<int64_t>(p.M) * p.K * 2 <= (32ll << 20);
+    p.group_m = env_gm > 0 ? env_gm : (a_fits_l2 ? p.tiles_m : 8);
+    if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+  }
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int waves = (tiles + max_pairs - 1) / max_pairs;
+  const double fill = static_cast<double>(tiles) / (static_cast<double>(waves) * max_pairs);
+  const bool sk = g_streamk_mode > 0 || (g_streamk_mode < 0 && fill < 0.96 && 2 * tiles >= max_pairs && num_kb >= 8);
+  if (sk && tiles % max_pairs != 0 && static_cast<int64_t>(tiles) * num_kb >= 4 * max_pairs) {
+    pairs = max_pairs;
+    const int full = tiles / pairs;
+    p.tiles_dp = full >= 1 ? (full - 1) * pairs : 0;
+    const int st = ensure_streamk_workspace(pairs);
+    if (st != MMPL_OK) return st;
+    p.sk_part = g_sk_part;
+    p.sk_flags = g_sk_flags;
+  }
   MMPL_CUDA_LAUNCH(launch_kernel(kern, 2 * pairs, kGemmThreads, kPairSmemBytes, stream, *ma, *mb, p));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;

@@ -9,6 +9,8 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
               int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
               const void* gate, int64_t gate_stride, int rows_per_frame, int force_bn, cudaStream_t stream);
 
+void gemm_set_streamk(int mode);  // -1 automatic (default), 0 off, 1 forced
+
 int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
                     int64_t ldkv0, int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1,
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
@@ -28,6 +30,8 @@ int qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, int64_
                     const int* kv_row, float eps, cudaStream_t st);
 int modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_t src_jstride, void* out, int F,
                    int J, int D, cudaStream_t st);
+// all blocks at once: out[l][f][6][D] = mods_dev[l][6][D] + src[f][6][D]; mods_dev = device table of L pointers
+int modulation_add_layers(const void* const* mods_dev, const void* src, void* out, int L, int F, int D, cudaStream_t st);
 int sinusoid_embedding(const double* t, void* out, int F, int dim, cudaStream_t st);
 int skinny_linear(const void* x, int64_t ldx, const void* w, const void* b, void* out, int64_t ldo, int M, int N,
                   int K, int silu_in, int silu_out, cudaStream_t st);

@@ -273,6 +273,32 @@ __global__ void modulation_add_kernel(const __nv_bfloat16* __restrict__ mod, con
   }
 }
 
+// The same for every block of the model in one launch: out[l][f][j][d] = bf16(mods[l][j][d] + src[f][j][d]) with
+// J = 6 (causal_model.py:300 evaluated for all CausalWanAttentionBlocks up front; e0 does not change inside a
+// forward). `mods` is a device table of the blocks' modulation parameters. blockIdx.y = block index.
+__global__ void modulation_add_layers_kernel(const __nv_bfloat16* const* __restrict__ mods,
+                                             const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out,
+                                             int F, int JD) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const __nv_bfloat16* mod = mods[blockIdx.y];
+  __nv_bfloat16* o = out + static_cast<int64_t>(blockIdx.y) * F * JD;
+  const int n8 = F * (JD / 8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += gridDim.x * blockDim.x) {
+    const int f = i / (JD / 8);
+    const int c = (i - f * (JD / 8)) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(mod + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(f) * JD + c);
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+    uint4 r;
+    uint32_t* rw = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rw[k] = pack_bf16x2(bf16_lo(aw[k]) + bf16_lo(bw[k]), bf16_hi(aw[k]) + bf16_hi(bw[k]));
+    *reinterpret_cast<uint4*>(o + static_cast<int64_t>(f) * JD + c) = r;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // sinusoidal_embedding_1d (model.py:15-25) in float64, cast to bf16 via float: out[f][0:half]=cos, [half:]=sin
 __global__ void sinusoid_kernel(const double* __restrict__ t, __nv_bfloat16* __restrict__ out, int F, int dim) {
@@ -494,6 +520,16 @@ int modulation_add(const void* mod, const void* src, int64_t src_fstride, int64_
   MMPL_CUDA_LAUNCH(launch_kernel(modulation_add_kernel, grid_for(n, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(mod),
                                                           static_cast<const __nv_bfloat16*>(src), src_fstride,
                                                           src_jstride, static_cast<__nv_bfloat16*>(out), F, J, D));
+  MMPL_CUDA(cudaGetLastError());
+  return MMPL_OK;
+}
+
+int modulation_add_layers(const void* const* mods_dev, const void* src, void* out, int L, int F, int D, cudaStream_t st) {
+  MMPL_CHECK(L > 0 && F > 0 && D > 0 && D % 8 == 0, MMPL_ERR_SHAPE, "modulation_add_layers: bad shape");
+  const int n8 = F * 6 * D / 8;
+  MMPL_CUDA_LAUNCH(launch_kernel(modulation_add_layers_kernel, dim3((n8 + 255) / 256, L), 256, 0, st,
+                                 reinterpret_cast<const __nv_bfloat16* const*>(mods_dev), static_cast<const __nv_bfloat16*>(src),
+                                 static_cast<__nv_bfloat16*>(out), F, 6 * D));
   MMPL_CUDA(cudaGetLastError());
   return MMPL_OK;
 }

@@ -75,6 +75,46 @@ def test_gemm_epilogues(M, N, K, tile):
     _report("gate_res_inplace", xres, ref, 4e-2, 2e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(4680, 1536, 1536), (4680, 1536, 8960), (4680, 4608, 1536), (10920, 5120, 5120),
+                                   (1170, 1536, 1536), (300, 512, 1024), (1998, 1280, 512)])
+def test_gemm_streamk_schedule(M, N, K):
+    """The stream-K tail schedule of the cta_group::2 kernel (gemm_tcgen05.cu: PairSched) against the whole-tile
+    schedule and the oracle: forced on (mode 1) for shapes of 1 ... 12 waves incl. fewer tiles than CTA pairs; repeated
+    launches and a CUDA-graph replay check that the hand-over flags are re-armed; results must be deterministic."""
+    from mmpl_b200 import _lib
+    ops, lib = _ops(), _lib.load()
+    x, w, b = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, scale=0.1, seed=3)
+    frames, fs = 3, M // 3
+    res, gate = _rand(M, N, seed=4), _rand(frames, N, seed=5)
+    ref = O.linear(x, w, b)
+    ref_gr = O.gate_residual(res, ref, gate, fs)
+    try:
+        lib.mmpl_gemm_set_streamk(0)
+        dp = ops.linear(x, w, b, tile_n=512)
+        lib.mmpl_gemm_set_streamk(1)
+        outs = [ops.linear(x, w, b, tile_n=512) for _ in range(3)]
+        gr = ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GATE_RES, residual=res, gate=gate, rows_per_frame=fs, tile_n=512)
+        gelu = ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GELU, tile_n=512)
+        out_g = torch.empty_like(outs[0])
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ops.linear(x, w, b, out=out_g, tile_n=512)
+            ops.linear(x, w, b, out=out_g, tile_n=512)
+        for _ in range(3):
+            out_g.zero_()
+            graph.replay()
+        torch.cuda.synchronize()
+    finally:
+        lib.mmpl_gemm_set_streamk(-1)
+    _report(f"streamk {M}x{N}x{K}", outs[0], ref, atol=2e-2, rtol=2e-2)
+    _report("streamk vs whole tiles", outs[0], dp, atol=2e-2, rtol=1e-2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "stream-K result changes between launches"
+    assert torch.equal(outs[0], out_g), "stream-K result differs under CUDA-graph replay"
+    _report("streamk gate_res", gr, ref_gr, 4e-2, 2e-2)
+    _report("streamk gelu", gelu, O.gelu_tanh(ref), 2e-2, 2e-2)
+
+
 @pytest.mark.parametrize("Lq,Lk,H", [(128, 128, 1), (256, 128, 2), (200, 300, 2), (390, 512, 2), (1170, 1170, 12),
                                      (4680, 4680, 12), (4680, 512, 12), (1560, 9360, 4)])
 def test_flash_attn(Lq, Lk, H):

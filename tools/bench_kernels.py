@@ -25,6 +25,31 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+def timeit_graph(fn, iters=20, reps=5):
+    """Same, but the `iters` launches are captured into a CUDA graph first: no CPU launch cost between kernels,
+    which is how they run inside mmpl_forward (back-to-back launches from C with programmatic dependent launch)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (iters * reps)
+
+
+if os.environ.get("BENCH_GRAPH", "1") != "0":
+    timeit = timeit_graph  # noqa: F811
+
+
 def bench_gemm(shapes, tiles):
     for (M, N, K) in shapes:
         nbuf = 4
