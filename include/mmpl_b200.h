@@ -66,7 +66,8 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
                     int64_t ldo, float softmax_scale, void* stream);
 
-/* Tuning / test hook: force the number of KV chunks each attention unit is split into (0 = cost model). */
+/* Tuning / test hook for the attention work partition: split > 0 forces the uniform schedule with that many KV chunks
+ * per unit; split < 0 forces the range schedule with -split heads per group; 0 = cost model (default). */
 int mmpl_attn_set_split(int split);
 /* Tuning / test hook: stream-K tail schedule of the cta_group::2 GEMM: 0 = never (default; slower on B200 at the
  * cfg2 shapes, see gemm_tcgen05.cu), -1 = automatic (when whole 256x256 tiles would leave more than 4 % of the last

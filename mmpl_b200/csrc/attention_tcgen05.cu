@@ -103,23 +103,88 @@ struct AttnParams {
   int seg_start[kMaxSeg];
   int seg_rows[kMaxSeg];
   int seg_src[kMaxSeg];
+  // range schedule (PieceIter): heads are taken in groups of `hg`; 0 = uniform-split schedule
+  int hg;
+  int G;          // CTAs of flash_attn_kernel (attn_combine_kernel needs it to locate the pieces of a unit)
 };
 
-// Piece pi (ordered head-major, then KV chunk, then query pair) -> unit, head, first tile, tile count, chunk.
-struct Piece { int u, head, q_row0, t0, n, chunk; };
-__device__ __forceinline__ Piece piece_info(const AttnParams& p, int pi) {
-  Piece pc;
-  const int per_head = p.split * p.QP;
-  pc.head = pi / per_head;
-  const int r = pi - pc.head * per_head;
-  pc.chunk = r / p.QP;
-  const int qp = r - pc.chunk * p.QP;
-  pc.u = pc.head * p.QP + qp;
-  pc.q_row0 = qp * (2 * kQTile);
-  pc.t0 = static_cast<int>(static_cast<long long>(pc.chunk) * p.T / p.split);
-  pc.n = static_cast<int>(static_cast<long long>(pc.chunk + 1) * p.T / p.split) - pc.t0;
-  return pc;
-}
+// A piece = KV tiles [t0, t0 + n) of one unit. `whole`: the piece is the entire unit and writes the normalised bf16
+// output; otherwise it leaves un-normalised fp32 O and (max, sum) in workspace slot `slot` for attn_combine_kernel.
+struct Piece { int head, q_row0, t0, n, slot; bool whole; };
+
+// Two schedules, chosen by the host (flash_attn_impl):
+//  * uniform split (hg == 0): every unit's KV range is cut into `split` equal chunks; pieces are ordered (head, chunk,
+//    query pair) and CTA b runs pieces b, b+G, ... Used for short KV ranges (cross-attention: 4 tiles per unit).
+//  * ranges (hg > 0): the heads are taken in groups of hg (sized so that a group's K/V stays L2-resident). Inside a
+//    group the (unit, KV tile) pairs, unit-major, form one sequence that is cut into G equal contiguous ranges, CTA c
+//    takes range c of every group in turn. All CTAs get the same number of KV tiles (228 units on 148 SMs is 1.54
+//    units each, which whole units or equal chunks can only approximate), and a CTA starts 2-3 pieces per group
+//    instead of one per chunk. A unit that straddles a range boundary is merged by attn_combine_kernel; the slot
+//    of a partial piece is (group, CTA, piece starts its CTA's range ? 0 : 1), so 2*G slots per group suffice.
+struct RangeGroup {
+  int heads, units;     // heads and units in this group
+  long long W;          // KV-tile units in this group = units * T
+  __device__ __forceinline__ void set(const AttnParams& p, int g) {
+    heads = min(p.hg, p.H - g * p.hg);
+    units = heads * p.QP;
+    W = static_cast<long long>(units) * p.T;
+  }
+  __device__ __forceinline__ long long lo(int c, int G) const { return c * W / G; }
+  // the CTA whose range contains position x: largest c with lo(c) <= x
+  __device__ __forceinline__ int cta_of(long long x, int G) const { return static_cast<int>(((x + 1) * G + W - 1) / W) - 1; }
+};
+
+struct PieceIter {
+  int G, c;
+  // uniform split
+  int pi;
+  // ranges
+  int g, ngroups;
+  long long pos, lo, hi;
+  RangeGroup grp;
+  __device__ __forceinline__ void init(const AttnParams& p, int cta, int grid) {
+    G = grid;
+    c = cta;
+    pi = cta;
+    g = -1;
+    ngroups = p.hg > 0 ? (p.H + p.hg - 1) / p.hg : 0;
+    pos = hi = lo = 0;
+  }
+  __device__ __forceinline__ bool next(const AttnParams& p, Piece& pc) {
+    if (p.hg == 0) {
+      if (pi >= p.n_pieces) return false;
+      const int per_head = p.split * p.QP;
+      pc.head = pi / per_head;
+      const int r = pi - pc.head * per_head;
+      const int chunk = r / p.QP;
+      const int qp = r - chunk * p.QP;
+      pc.q_row0 = qp * (2 * kQTile);
+      pc.t0 = static_cast<int>(static_cast<long long>(chunk) * p.T / p.split);
+      pc.n = static_cast<int>(static_cast<long long>(chunk + 1) * p.T / p.split) - pc.t0;
+      pc.slot = (pc.head * p.QP + qp) * p.split + chunk;
+      pc.whole = p.split == 1;
+      pi += G;
+      return true;
+    }
+    while (pos >= hi) {
+      if (++g >= ngroups) return false;
+      grp.set(p, g);
+      lo = pos = grp.lo(c, G);
+      hi = grp.lo(c + 1, G);
+    }
+    const int ul = static_cast<int>(pos / p.T);
+    const int head_l = ul / p.QP;
+    pc.head = g * p.hg + head_l;
+    pc.q_row0 = (ul - head_l * p.QP) * (2 * kQTile);
+    pc.t0 = static_cast<int>(pos - static_cast<long long>(ul) * p.T);
+    const long long end = min(hi, static_cast<long long>(ul + 1) * p.T);
+    pc.n = static_cast<int>(end - pos);
+    pc.whole = pc.n == p.T;
+    pc.slot = (g * G + c) * 2 + (pos == lo ? 0 : 1);
+    pos = end;
+    return true;
+  }
+};
 
 // Select over the (at most 8) segment parameters without indexing the kernel-parameter arrays dynamically
 // (a dynamic index would make the compiler copy them to local memory).
@@ -229,8 +294,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // -------------------------------------------------------- TMA producer
       // (whole warp, converged; one elected lane issues each TMA: see the "_elect" wrappers in ptx.cuh)
       int g = 0, piece = 0;
-      for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
-        const Piece pc = piece_info(p, pi);
+      PieceIter pit;
+      pit.init(p, blockIdx.x, G);
+      Piece pc;
+      for (; pit.next(p, pc); ++piece) {
         const int t0 = pc.t0, n = pc.n, head = pc.head, q_row0 = pc.q_row0;
         mbar_wait(q_empty, (piece & 1) ^ 1);
         mbar_arrive_expect_tx_elect(q_full, 4 * kBoxBytes);
@@ -294,8 +361,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const long long tm_begin = clock64();
 #endif
       int g = 0, piece = 0;
-      for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
-        const int n = piece_info(p, pi).n;
+      PieceIter pit;
+      pit.init(p, blockIdx.x, G);
+      Piece pc;
+      for (; pit.next(p, pc); ++piece) {
+        const int n = pc.n;
         mbar_wait(q_full, piece & 1);
         mbar_wait(&k_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
@@ -372,9 +442,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     long long dbg[4] = {0, 0, 0, 0};
 #endif
     int g = 0, piece = 0;
-    for (int pi = blockIdx.x; pi < p.n_pieces; pi += G, ++piece) {
-      const Piece pc = piece_info(p, pi);
-      const int u = pc.u, t0 = pc.t0, n = pc.n, head = pc.head;
+    PieceIter pit;
+    pit.init(p, blockIdx.x, G);
+    Piece pc;
+    for (; pit.next(p, pc); ++piece) {
+      const int t0 = pc.t0, n = pc.n, head = pc.head;
       const int q_row = pc.q_row0 + row_in_unit;
       float m_run = -INFINITY;  // running max, in the scaled log2 domain
       float l_run = 0.f;
@@ -466,35 +538,38 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // piece epilogue
       mbar_wait(o_full, piece & 1);
       tc_fence_after();
-      if (p.split == 1) {
+      if (pc.whole) {
         // whole unit: O / l -> bf16 -> out[q_row, head*128 : head*128+128]
         const float inv_l = 1.0f / l_run;
         __nv_bfloat16* orow = p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD;
         const bool wide_out = (p.ldo % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0);
+        // the TMEM loads are issued two at a time before a wait (the S registers are dead here): two TMEM round trips
+        // instead of four on the critical path between two pieces
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(t_o + c * 32, o);
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t o[64];
+          tmem_ld_32x32(t_o + c2 * 64, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+          tmem_ld_32x32(t_o + c2 * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
           tmem_ld_wait();
           if (q_row < p.Lq) {
 #pragma unroll
-            for (int gq = 0; gq < 2; ++gq) {
+            for (int gq = 0; gq < 4; ++gq) {
               uint32_t w[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 w[i] = pack_bf16x2(__uint_as_float(o[gq * 16 + 2 * i]) * inv_l, __uint_as_float(o[gq * 16 + 2 * i + 1]) * inv_l);
               if (wide_out) {
-                st_global_v8(orow + c * 32 + gq * 16, w);
+                st_global_v8(orow + c2 * 64 + gq * 16, w);
               } else {
-                *reinterpret_cast<uint4*>(orow + c * 32 + gq * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(orow + c * 32 + gq * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                *reinterpret_cast<uint4*>(orow + c2 * 64 + gq * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(orow + c2 * 64 + gq * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
               }
             }
           }
         }
       } else {
         // partial unit: un-normalised fp32 O and (m, l) to the workspace slot of this piece
-        const int64_t base = (static_cast<int64_t>(u) * p.split + pc.chunk) * kUnitRows + row_in_unit;
+        const int64_t base = static_cast<int64_t>(pc.slot) * kUnitRows + row_in_unit;
         float* po = p.part_o + base * kHD;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -531,6 +606,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
 // Merges the pieces of every unit that was split across CTAs:
 //   out = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i,  M = max_i m_i.   One warp per query row.
+// The pieces of unit u: uniform split -> slots u*split + i; range schedule -> one per CTA whose range of the unit's
+// head group overlaps the unit (same arithmetic as PieceIter), none if a single CTA ran the whole unit.
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const AttnParams p) {
   pdl_wait();
@@ -538,17 +615,41 @@ attn_combine_kernel(const AttnParams p) {
   const int u = blockIdx.x >> 5;
   const int row_in_unit = (blockIdx.x & 31) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int np = p.split;
   const int head = u / p.QP;
   const int q_row = (u - head * p.QP) * kUnitRows + row_in_unit;
+  // piece i of the unit -> workspace slot, or -1 (range schedule: a CTA whose range is empty holds no piece)
+  int np, c_first = 0, g = 0;
+  long long start = 0;
+  RangeGroup grp;
+  if (p.hg == 0) {
+    np = p.split;
+  } else {
+    g = head / p.hg;
+    grp.set(p, g);
+    start = static_cast<long long>(u - g * p.hg * p.QP) * p.T;
+    c_first = grp.cta_of(start, p.G);
+    np = grp.cta_of(start + p.T - 1, p.G) - c_first + 1;
+    if (np == 1) return;  // written directly by the CTA that ran the whole unit
+  }
   if (q_row >= p.Lq) return;
-  const int64_t base = static_cast<int64_t>(u) * p.split * kUnitRows + row_in_unit;
+  auto slot_of = [&](int i) -> int {
+    if (p.hg == 0) return u * p.split + i;
+    const int c = c_first + i;
+    const long long lo = grp.lo(c, p.G);
+    if (grp.lo(c + 1, p.G) <= lo) return -1;
+    return (g * p.G + c) * 2 + (max(lo, start) == lo ? 0 : 1);  // same rule as PieceIter: does the piece open its CTA's range?
+  };
   float M = -INFINITY;
-  for (int i = 0; i < np; ++i) M = fmaxf(M, p.part_ml[(base + static_cast<int64_t>(i) * kUnitRows) * 2]);
+  for (int i = 0; i < np; ++i) {
+    const int sl = slot_of(i);
+    if (sl >= 0) M = fmaxf(M, p.part_ml[(static_cast<int64_t>(sl) * kUnitRows + row_in_unit) * 2]);
+  }
   float L = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = 0; i < np; ++i) {
-    const int64_t r = base + static_cast<int64_t>(i) * kUnitRows;
+    const int sl = slot_of(i);
+    if (sl < 0) continue;
+    const int64_t r = static_cast<int64_t>(sl) * kUnitRows + row_in_unit;
     const float2 ml = *reinterpret_cast<const float2*>(p.part_ml + r * 2);
     const float w = exp2f(ml.x - M);
     L += w * ml.y;
@@ -599,32 +700,63 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   const CUtensorMap* mv1 = uses1 ? get_tensor_map_bf16(v1, rows1, static_cast<uint64_t>(H) * kHD, ldkv1, 128) : mv0;
   if (!mq || !mk0 || !mv0 || !mk1 || !mv1) return MMPL_ERR_CUDA;
 
-  // work partition: U units of T tiles, each cut into `split` KV chunks, over G persistent CTAs.
-  // Cost model (in KV-tile times per SM): rounds * (tiles per piece + fixed cost per piece) + merge traffic.
+  // work partition: U units of T KV tiles over G persistent CTAs, by one of the two schedules of PieceIter.
+  // Cost model (in KV-tile times per SM; measured on B200 with tools/bench_kernels.py): a piece costs ~6 tile times on
+  // top of its tiles (Q load, pipeline fill, epilogue); merging costs 2 x 128 KB of traffic per partial piece ~ 0.029
+  // tile times each.
   p.QP = (Lq + kUnitRows - 1) / kUnitRows;
   p.T = T;
   const int U = p.QP * H;
   const int sms = sm_count();
+  const double piece_fixed = 6.0, merge_per_piece = 0.0291, merge_fixed = 6.0;  // merge_fixed: the combine launch itself
   int best_split = 1;
-  {
-    // measured on B200 (tools/bench_kernels.py): a piece costs ~6 tile times on top of its tiles (Q load, pipeline
-    // fill, epilogue); merging costs 2 x 128 KB of HBM traffic per (unit, chunk) ~ 0.029 tile times each.
-    const double piece_fixed = 6.0;
-    double best = 1e30;
-    for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
-      if (sp > 1 && T / sp < 8) break;
-      const int rounds = (U * sp + sms - 1) / sms;
-      const double cost = rounds * (static_cast<double>(T) / sp + piece_fixed) + (sp > 1 ? 0.0291 * U * sp : 0.0);
-      if (cost < best - 1e-9) { best = cost; best_split = sp; }
-    }
+  double best = 1e30;
+  for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
+    if (sp > 1 && T / sp < 8) break;
+    const int rounds = (U * sp + sms - 1) / sms;
+    const double cost = rounds * (static_cast<double>(T) / sp + piece_fixed) + (sp > 1 ? merge_fixed + merge_per_piece * U * sp : 0.0);
+    if (cost < best - 1e-9) { best = cost; best_split = sp; }
   }
-  if (force_split > 0 && force_split <= T) best_split = force_split;
-  p.split = best_split;
-  p.n_pieces = U * p.split;
+  // Range schedule. Its CTAs sit at different KV positions of the same head, so (unlike the uniform schedule, whose
+  // CTAs stream the same K/V tiles in lockstep and are served by L2 together) it pays only while the K/V of all heads
+  // stays L2-resident: measured on B200 (profiles/README.md) 6 % faster than the best uniform split for L_kv = 9360
+  // and 14040 at cfg2 (58 / 86 MB of K/V), slower from 115 MB up, erratic with several head groups. Hence: one group
+  // of all heads, only below the L2 budget, and only when the cost model prefers it.
+  int hg = 0;
+  {
+    static const int l2_mb = getenv("MMPL_ATTN_L2_MB") ? atoi(getenv("MMPL_ATTN_L2_MB")) : 90;
+    static const int mode_env = getenv("MMPL_ATTN_RANGES") ? atoi(getenv("MMPL_ATTN_RANGES")) : -1;  // 0 never, 1 whenever possible, -1 cost model
+    const double kv_mb = static_cast<double>(H) * T * kKVTile * 512.0 / (1 << 20);
+    const double pieces_per_cta = static_cast<double>(U) / sms + 1.0;
+    const double cost_ranges = static_cast<double>(U) * T / sms + piece_fixed * pieces_per_cta + merge_fixed + merge_per_piece * 2.0 * sms;
+    const bool possible = T >= 16 && static_cast<long long>(U) * T >= 8ll * sms && kv_mb <= l2_mb;
+    if (possible && (mode_env == 1 || (mode_env < 0 && cost_ranges < best))) hg = H;
+  }
+  if (force_split > 0 && force_split <= T) {
+    best_split = force_split;
+    hg = 0;
+  } else if (force_split < 0 && T >= 2 && static_cast<long long>(U) * T >= 2ll * sms) {
+    hg = -force_split < H ? -force_split : H;  // test hook: range schedule with this many heads per group
+  }
   static const bool nonpersistent = getenv("MMPL_ATTN_NONPERSISTENT") != nullptr;
-  const int G = (p.n_pieces < sms || nonpersistent) ? p.n_pieces : sms;
-  if (p.split > 1) {
-    const size_t need = static_cast<size_t>(U) * p.split * kUnitRows * (kHD + 2) * sizeof(float);
+  int G;
+  size_t slots = 0;
+  if (hg > 0) {
+    p.hg = hg;
+    p.split = 1;
+    p.n_pieces = 0;
+    G = sms;
+    slots = static_cast<size_t>((H + hg - 1) / hg) * G * 2;
+  } else {
+    p.hg = 0;
+    p.split = best_split;
+    p.n_pieces = U * p.split;
+    G = (p.n_pieces < sms || nonpersistent) ? p.n_pieces : sms;
+    slots = p.split > 1 ? static_cast<size_t>(U) * p.split : 0;
+  }
+  p.G = G;
+  if (slots > 0) {
+    const size_t need = slots * kUnitRows * (kHD + 2) * sizeof(float);
     if (need > g_part_bytes) {
       if (g_part) MMPL_CUDA(cudaFree(g_part));
       g_part = nullptr;
@@ -633,7 +765,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
       g_part_bytes = need;
     }
     p.part_o = g_part;
-    p.part_ml = g_part + static_cast<size_t>(U) * p.split * kUnitRows * kHD;
+    p.part_ml = g_part + slots * kUnitRows * kHD;
   }
 
   static bool attr_set = false;
@@ -643,7 +775,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   }
   MMPL_CUDA_LAUNCH(launch_kernel(flash_attn_kernel, G, kAttnThreads, kAttnSmem, stream, *mq, *mk0, *mv0, *mk1, *mv1, p));
   MMPL_CUDA(cudaGetLastError());
-  if (p.split > 1) {
+  if (slots > 0) {
     MMPL_CUDA_LAUNCH(launch_kernel(attn_combine_kernel, U * 32, 256, 0, stream, p));
     MMPL_CUDA(cudaGetLastError());
   }

@@ -718,7 +718,20 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     MMPL_CHECK(gate != nullptr && rows_per_frame > 0 && gate_stride % 8 == 0, MMPL_ERR_ARG,
                "gemm: gate epilogue needs gate, rows_per_frame > 0 and gate_stride %% 8 == 0");
   // tile_n 512 selects the cta_group::2 kernel (256 x 256 tile per CTA pair); auto-selected for large problems
-  const bool use_pair = force_bn == 512 || (force_bn == 0 && N % 256 == 0 && M >= 512);
+  bool use_pair = force_bn == 512 || (force_bn == 0 && N % 256 == 0 && M >= 512);
+  if (use_pair && force_bn == 0 && K <= 2048) {
+    // Short-K problems whose 256 x 256 tiles leave the last wave mostly empty while 128 x 128 tiles fill theirs:
+    // cfg2's o / cross-attention projections (M = 4680, N = K = 1536) are 114 pair tiles on 74 pairs (1.54 waves) but
+    // 444 = 3 x 148 single-CTA tiles; measured 20.3 us against 22.3 us. With a long K the pair kernel still wins.
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int tp = ((M + 255) / 256) * (N / 256), ts = ((M + kBM - 1) / kBM) * (N / 128);
+    const double fill_pair = double(tp) / (double((tp + sms / 2 - 1) / (sms / 2)) * (sms / 2));
+    const double fill_single = double(ts) / (double((ts + sms - 1) / sms) * sms);
+    if (fill_pair < 0.8 && fill_single > 0.95) {
+      use_pair = false;
+      force_bn = 128;
+    }
+  }
   if (use_pair) {
     MMPL_CHECK(N % 8 == 0, MMPL_ERR_SHAPE, "gemm: N must be a multiple of 8");
     const CUtensorMap* pa = get_tensor_map_bf16(a, M, K, lda, kBM);

@@ -106,7 +106,7 @@ def test_gemm_streamk_schedule(M, N, K):
             graph.replay()
         torch.cuda.synchronize()
     finally:
-        lib.mmpl_gemm_set_streamk(-1)
+        lib.mmpl_gemm_set_streamk(0)  # the library default
     _report(f"streamk {M}x{N}x{K}", outs[0], ref, atol=2e-2, rtol=2e-2)
     _report("streamk vs whole tiles", outs[0], dp, atol=2e-2, rtol=1e-2)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "stream-K result changes between launches"
@@ -156,6 +156,33 @@ def test_flash_attn_forced_kv_split(split):
         lib.mmpl_attn_set_split(0)
     idx = torch.cat([torch.arange(0, 1300), torch.arange(2000, 4900)]).to(DEV)
     _report(f"attn split={split}", got, O.attention(q, k[idx], v[idx]), atol=1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("Lq,Lk,H,hg", [(700, 5000, 3, 1), (700, 5000, 3, 2), (700, 5000, 3, 3), (4680, 4680, 12, 12),
+                                        (4680, 9360, 12, 5), (1560, 20000, 4, 1), (300, 2100, 2, 2), (3120, 14040, 8, 3)])
+def test_flash_attn_range_schedule(Lq, Lk, H, hg):
+    """The range schedule (attention_tcgen05.cu: PieceIter with hg > 0): every CTA takes an equal contiguous range of
+    each head group's (unit, KV tile) sequence; units that straddle a range boundary are merged by the combine
+    kernel. Forced with a negative split (= heads per group), incl. group sizes that do not divide the head count,
+    against the oracle and against the whole-unit schedule; also over row segments."""
+    from mmpl_b200 import _lib
+    ops, lib = _ops(), _lib.load()
+    q, k, v = _rand(Lq, H, 128, seed=1), _rand(Lk, H, 128, seed=2), _rand(Lk, H, 128, seed=3)
+    segs = [(0, Lk // 3 + 17), (Lk // 2, Lk // 2 - 5)]
+    idx = torch.cat([torch.arange(a, a + n) for a, n in segs]).to(DEV)
+    try:
+        lib.mmpl_attn_set_split(1)
+        whole = ops.flash_attn(q, k, v)
+        lib.mmpl_attn_set_split(-hg)
+        got = ops.flash_attn(q, k, v)
+        got2 = ops.flash_attn(q, k, v)
+        got_seg = ops.flash_attn(q, k, v, segments=segs)
+    finally:
+        lib.mmpl_attn_set_split(0)
+    _report(f"attn ranges hg={hg} {Lq}x{Lk}x{H}", got, O.attention(q, k, v), atol=1e-2, rtol=2e-2)
+    _report("ranges vs whole units", got, whole, atol=1e-2, rtol=2e-2)
+    assert torch.equal(got, got2), "range schedule is not deterministic"
+    _report("ranges over segments", got_seg, O.attention(q, k[idx], v[idx]), atol=1e-2, rtol=2e-2)
 
 
 def test_flash_attn_large_logits():

@@ -96,6 +96,9 @@ def bench_attn(cases):
             line += f" split{sp}: {ms * 1e3:7.1f} us {4 * Lq * Lk * H * 128 / ms / 1e9:6.1f} |"
             print(f"  [{Lq}x{Lk}x{H}] split{sp}: {ms * 1e3:7.1f} us", flush=True)
         lib.mmpl_attn_set_split(0)
+        if os.environ.get("ATTN_NO_FA2"):
+            print(line, flush=True)
+            continue
         try:
             from flash_attn import flash_attn_func
             ms2 = timeit(lambda: flash_attn_func(q[None], k[None], v[None]), iters=10)
@@ -114,4 +117,7 @@ if __name__ == "__main__":
                     (10920, 15360, 5120), (10920, 5120, 5120), (10920, 13824, 5120), (10920, 5120, 13824)],
                    tiles=[128, 256, 512])
     if "attn" in a.what:
-        bench_attn([(4680, 4680, 12), (4680, 18720, 12), (4680, 32760, 12), (4680, 512, 12), (10920, 14040, 40)])
+        shapes = [(4680, 4680, 12), (4680, 18720, 12), (4680, 32760, 12), (4680, 512, 12), (10920, 14040, 40)]
+        if os.environ.get("ATTN_SHAPES"):  # e.g. "4680x9360x12,4680x14040x12"
+            shapes = [tuple(int(v) for v in sh.split("x")) for sh in os.environ["ATTN_SHAPES"].split(",")]
+        bench_attn(shapes)
