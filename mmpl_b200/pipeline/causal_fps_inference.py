@@ -20,6 +20,7 @@ from __future__ import annotations
 from typing import Callable, List, Optional
 
 import torch
+import torch.distributed as dist
 
 from ..unipc import FlowUniPCMultistepScheduler
 from ..wan_wrapper import WanFPSWrapper
@@ -33,11 +34,24 @@ I2V_STAGE_FRAMES = [1, 1, 7, 6, 6]
 
 class CausalFPSInferencePipeline(torch.nn.Module):
     def __init__(self, args, device, generator=None, text_encoder=None, vae=None, device_cond="cuda:0",
-                 device_uncond="cuda:0", save="latents_chunk1.pt", anchor_sink: Optional[Callable] = None):
+                 device_uncond="cuda:0", save="latents_chunk1.pt", anchor_sink: Optional[Callable] = None,
+                 cfg_group: Optional["dist.ProcessGroup"] = None):
         super().__init__()
         self.need_wait = False
         self.save = save
         self.anchor_sink = anchor_sink
+        # CFG-pair split (the reference's device_cond / device_uncond hooks, :42-43,346-367, taken to one
+        # process per GPU): `cfg_group` is a process group of exactly two ranks. Rank 0 of the group runs the
+        # conditional forwards with kv_cache_pos, rank 1 the unconditional ones with kv_cache_neg; after every
+        # denoising forward the two flow predictions ([B, n, 16, H, W] bf16, <= 1.4 MB) are exchanged with one
+        # all-gather and both ranks apply the same CFG combine and UniPC update, so their latents stay identical.
+        # Both ranks must be constructed and called with the same seeds (the pipeline draws noise with torch.randn_like).
+        self.cfg_group = cfg_group
+        self.cfg_role = None
+        if cfg_group is not None:
+            if dist.get_world_size(cfg_group) != 2:
+                raise ValueError("cfg_group must contain exactly two ranks (conditional, unconditional)")
+            self.cfg_role = dist.get_rank(cfg_group)
         self.device_cond = device_cond
         self.device_uncond = device_uncond
         if torch.device(device_cond) != torch.device(device_uncond):
@@ -108,15 +122,17 @@ class CausalFPSInferencePipeline(torch.nn.Module):
         output = torch.zeros([batch_size, num_output_frames, num_channels, height, width], device=noise.device,
                              dtype=noise.dtype)
 
-        if self.kv_cache_pos is None or self.kv_cache_pos[0]["k"].shape[0] != batch_size:
+        self.cfg_bytes_exchanged = 0
+        own = self.kv_cache_neg if self.cfg_role == 1 else self.kv_cache_pos
+        if own is None or own[0]["k"].shape[0] != batch_size:
             self._initialize_kv_cache(batch_size=batch_size, dtype=noise.dtype, device=noise.device)
             self._initialize_crossattn_cache(batch_size=batch_size, dtype=noise.dtype, device=noise.device)
         else:
-            for block_index in range(self.num_transformer_blocks):
-                self.crossattn_cache_pos[block_index]["is_init"] = False
-                self.crossattn_cache_neg[block_index]["is_init"] = False
+            for cross in (self.crossattn_cache_pos, self.crossattn_cache_neg):
+                for block in cross or []:
+                    block["is_init"] = False
             for cache, dev in ((self.kv_cache_pos, self.device_cond), (self.kv_cache_neg, self.device_uncond)):
-                for block in cache:
+                for block in cache or []:
                     block["global_end_index"] = torch.tensor([0], dtype=torch.long, device=dev)
                     block["local_end_index"] = torch.tensor([0], dtype=torch.long, device=dev)
                     block["attention_vis_index"] = []
@@ -129,8 +145,21 @@ class CausalFPSInferencePipeline(torch.nn.Module):
         if self.independent_first_frame and initial_latent is None:
             all_num_frames = [1] + all_num_frames
 
-        def both(latents, timestep, frames):
+        def both(latents, timestep, frames, need_flow=True):
             cur = [i * fs for i in frames]
+            if self.cfg_group is not None:
+                cond = self.cfg_role == 0
+                flow, _ = self.generator_cond(
+                    noisy_image_or_video=latents, conditional_dict=conditional_dict if cond else unconditional_dict,
+                    timestep=timestep, kv_cache=self.kv_cache_pos if cond else self.kv_cache_neg,
+                    crossattn_cache=self.crossattn_cache_pos if cond else self.crossattn_cache_neg,
+                    current_start=cur, cache_start=cur)
+                if not need_flow:
+                    return None, None  # clean-context pass: only the K/V written into this rank's cache matter
+                pair = [torch.empty_like(flow), torch.empty_like(flow)]
+                dist.all_gather(pair, flow.contiguous(), group=self.cfg_group)
+                self.cfg_bytes_exchanged += flow.numel() * flow.element_size()
+                return pair[0], pair[1]
             flow_c, _ = self.generator_cond(noisy_image_or_video=latents, conditional_dict=conditional_dict,
                                             timestep=timestep, kv_cache=self.kv_cache_pos,
                                             crossattn_cache=self.crossattn_cache_pos, current_start=cur, cache_start=cur)
@@ -158,7 +187,7 @@ class CausalFPSInferencePipeline(torch.nn.Module):
                         torch.randn_like(latents[:, -1:]).flatten(0, 1),
                         self.ddmp_timestep.flatten(0, 1).to(latents.device)).unflatten(0, (batch_size, 1))
                     for cache in (self.kv_cache_pos, self.kv_cache_neg):
-                        for block in cache:
+                        for block in cache or []:
                             for val in target_values:
                                 present = val in block["attention_vis_index"]
                                 if global_chunk_index == 2 and present:
@@ -183,22 +212,22 @@ class CausalFPSInferencePipeline(torch.nn.Module):
                     if self.anchor_sink is not None:
                         self.anchor_sink(save_latents)
                 # Step 3.3: clean-context pass at t=0 for both caches (:386-403)
-                both(latents, timestep * 0, current_start_frame)
+                both(latents, timestep * 0, current_start_frame, need_flow=False)
                 global_chunk_index += 1
             else:
                 # prefill with the given first frame(s) instead of generating stage 0 (:407-439; MMPL_i2v :368-435)
                 timestep = 0 * torch.ones([batch_size, current_num_frames], device=noise.device, dtype=torch.float32)
                 if i2v and initial_latent.shape[1] > 1:
                     for step in range(2):  # "segment connect": two frames, one slot each
-                        both(initial_latent[:, step:step + 1], timestep * 0, result[step])
+                        both(initial_latent[:, step:step + 1], timestep * 0, result[step], need_flow=False)
                         output[:, result[step]] = initial_latent[:, step:step + 1]
                     global_chunk_index = 2
                 elif i2v:
-                    both(initial_latent[:, 0:1], timestep * 0, result[0])
+                    both(initial_latent[:, 0:1], timestep * 0, result[0], need_flow=False)
                     output[:, result[0]] = initial_latent
                     global_chunk_index += 1
                 else:
-                    both(initial_latent, timestep * 0, result[0])
+                    both(initial_latent, timestep * 0, result[0], need_flow=False)
                     output[:, result[global_chunk_index]] = initial_latent
                     global_chunk_index += 1
 
@@ -224,8 +253,9 @@ class CausalFPSInferencePipeline(torch.nn.Module):
                 "attention_vis_index": [],
             } for _ in range(self.num_transformer_blocks)]
 
-        self.kv_cache_pos = make(self.device_cond)
-        self.kv_cache_neg = make(self.device_uncond)
+        # under the CFG-pair split a rank holds only the cache of its own branch
+        self.kv_cache_pos = make(self.device_cond) if self.cfg_role in (None, 0) else None
+        self.kv_cache_neg = make(self.device_uncond) if self.cfg_role in (None, 1) else None
 
     def _initialize_crossattn_cache(self, batch_size, dtype, device):
         """:484-501."""
@@ -239,8 +269,8 @@ class CausalFPSInferencePipeline(torch.nn.Module):
                 "is_init": False,
             } for _ in range(self.num_transformer_blocks)]
 
-        self.crossattn_cache_pos = make(self.device_cond)
-        self.crossattn_cache_neg = make(self.device_uncond)
+        self.crossattn_cache_pos = make(self.device_cond) if self.cfg_role in (None, 0) else None
+        self.crossattn_cache_neg = make(self.device_uncond) if self.cfg_role in (None, 1) else None
 
     def _initialize_sample_scheduler(self, noise):
         """:503-512 (unipc branch)."""

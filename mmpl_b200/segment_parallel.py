@@ -6,6 +6,12 @@ pipeline/casual_fps_inference.py:380-383). Here every GPU is one process (torchr
 the hand-off is a point-to-point message on the communicator (NCCL over NVLink on GPUs: the send is enqueued on the
 compute stream right after the anchor stage, so the producer continues with its next stage immediately; gloo in the CPU
 tests). The path has no other exchange: each rank holds a full replica and its own caches.
+
+With the CFG-pair split (`lanes=2`; CausalFPSInferencePipeline(cfg_group=...)) a segment runs on two consecutive
+ranks -- lane 0 the conditional branch, lane 1 the unconditional one -- which hold identical latents, so each lane
+hands its copy of the anchors to the same lane of the next segment's pair. One prompt's chain saturates at
+T_segment / T_anchor ~ 3 segment slots; the pair split halves both times, which is what lets one
+chain use 8 GPUs (4 slots x 2 lanes).
 """
 from __future__ import annotations
 
@@ -18,13 +24,15 @@ T2V_ANCHOR_SHAPE = (1, 8, 16, 60, 104)   # frame 0 + stage-1 frames [2,3,10,11,1
 I2V_ANCHOR_SHAPE = (1, 3, 16, 60, 104)   # frames 0, 19, 20                               (0.6 MB bf16)
 
 
-def segments_of_rank(rank: int, world: int, num_segments: int) -> List[int]:
-    """Round-robin placement: rank r runs segments r, r+G, r+2G, ... (the 5-60s driver's rotation, :231-238)."""
-    return list(range(rank, num_segments, world))
+def segments_of_rank(rank: int, world: int, num_segments: int, lanes: int = 1) -> List[int]:
+    """Round-robin placement: slot s = rank // lanes runs segments s, s+G, s+2G, ... with G = world // lanes slots
+    (the 5-60s driver's rotation, :231-238)."""
+    return list(range(rank // lanes, num_segments, world // lanes))
 
 
-def producer_of(segment: int, world: int) -> int:
-    return segment % world
+def producer_of(segment: int, world: int, lanes: int = 1, lane: int = 0) -> int:
+    """Rank that runs `segment` (its lane `lane` under the CFG-pair split)."""
+    return (segment % (world // lanes)) * lanes + lane
 
 
 def default_segment_connect(anchors: torch.Tensor) -> torch.Tensor:
@@ -37,16 +45,20 @@ def default_segment_connect(anchors: torch.Tensor) -> torch.Tensor:
 class AnchorChannel:
     """Point-to-point hand-off of one segment's anchor latents to the rank that runs the next segment."""
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, lanes: int = 1):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world % lanes:
+            raise ValueError(f"world size {self.world} is not a multiple of lanes={lanes}")
+        self.lanes = lanes
+        self.lane = self.rank % lanes
         self._local: Dict[int, torch.Tensor] = {}
         self._pending = []
         self.bytes_sent = 0
 
     def send(self, anchors: torch.Tensor, segment: int) -> None:
-        dst = producer_of(segment + 1, self.world)
+        dst = producer_of(segment + 1, self.world, self.lanes, self.lane)
         payload = anchors.contiguous()
         self.bytes_sent += payload.numel() * payload.element_size()
         if dst == self.rank:
@@ -55,7 +67,7 @@ class AnchorChannel:
         self._pending.append((dist.isend(payload, dst=dst, group=self.group, tag=segment + 1), payload))
 
     def recv(self, segment: int, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Tensor:
-        src = producer_of(segment - 1, self.world)
+        src = producer_of(segment - 1, self.world, self.lanes, self.lane)
         if src == self.rank:
             return self._local.pop(segment)
         buf = torch.empty(tuple(shape), dtype=dtype, device=device)
@@ -85,19 +97,19 @@ class SegmentParallelRunner:
     def run(self, make_noise: Callable[[int], torch.Tensor], text_prompts: List[str], num_segments: int) -> Dict[int, torch.Tensor]:
         ch = self.channel
         outputs: Dict[int, torch.Tensor] = {}
-        for seg in segments_of_rank(ch.rank, ch.world, num_segments):
+        for seg in segments_of_rank(ch.rank, ch.world, num_segments, ch.lanes):
             noise = make_noise(seg)
             initial = None
             if seg > 0:
                 anchors = ch.recv(seg, (noise.shape[0],) + self.anchor_shape[1:3] + tuple(noise.shape[3:]), noise.dtype, noise.device)
                 initial = self.connect(anchors)
-                self.log.append(("recv", seg, producer_of(seg - 1, ch.world)))
+                self.log.append(("recv", seg, producer_of(seg - 1, ch.world, ch.lanes, ch.lane)))
             has_next = seg + 1 < num_segments
 
             def sink(payload, seg=seg, has_next=has_next):
                 if has_next:
                     ch.send(payload, seg)
-                    self.log.append(("send", seg, producer_of(seg + 1, ch.world)))
+                    self.log.append(("send", seg, producer_of(seg + 1, ch.world, ch.lanes, ch.lane)))
 
             self.pipeline.anchor_sink = sink
             _, latents = self.pipeline.inference(noise=noise, text_prompts=text_prompts, initial_latent=initial,

@@ -90,3 +90,99 @@ def test_single_rank_runs_all_segments_locally():
     assert sorted(outs) == [0, 1, 2] and outs[2][0, 0, 0, 0, 0].item() == 2.0 and outs[2][0, 5, 0, 0, 0].item() == 1.0
     a = torch.arange(8.).view(1, 8, 1, 1, 1)
     assert default_segment_connect(a).flatten().tolist() == [6.0, 7.0]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CFG-pair split: conditional / unconditional branch on two ranks, flow all-gather per step
+def _fps_pipeline(cfg_group=None):
+    import types
+
+    from mmpl_b200.pipeline import CausalFPSInferencePipeline
+    from mmpl_b200.scheduler import FlowMatchScheduler
+
+    class CpuScheduler(FlowMatchScheduler):
+        def add_noise(self, original_samples, noise, timestep):  # torch restatement of the CUDA kernel, CPU
+            sigma = self.sigmas[self.timestep_id(timestep.float())].reshape(-1, 1, 1, 1)
+            return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
+
+    class FakeGenerator(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = types.SimpleNamespace(num_layers=3, local_attn_size=-1, num_heads=2, dim=256, text_len=32,
+                                               num_frame_per_block=1)
+            self.scheduler = CpuScheduler(shift=5.0, sigma_min=0.0, extra_one_step=True)
+            self.scheduler.set_timesteps(1000, training=True)
+
+        def get_scheduler(self):
+            return self.scheduler
+
+    gen = FakeGenerator()
+    tags = []
+
+    def fwd(noisy_image_or_video, conditional_dict, timestep, kv_cache, crossattn_cache, current_start, cache_start):
+        tags.append(conditional_dict["tag"])
+        assert kv_cache is not None and crossattn_cache is not None
+        sign = 1.0 if conditional_dict["tag"] == "pos" else -0.5
+        return noisy_image_or_video * 0.1 + sign * 0.01 * float(timestep.flatten()[0]) / 1000.0, None
+
+    gen.forward = fwd
+    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="neg",
+                                 independent_first_frame=False, sampling_steps=3, model_kwargs={})
+    text = lambda text_prompts: {"tag": "neg" if text_prompts[0] == "neg" else "pos"}  # noqa: E731
+    vae = types.SimpleNamespace(decode_to_pixel=lambda latents, use_cache=False: latents)
+    torch.manual_seed(11)  # constructor randint + the re-noising randn_like draws: same stream on both lanes
+    pipe = CausalFPSInferencePipeline(args, torch.device("cpu"), generator=gen, text_encoder=text, vae=vae,
+                                      device_cond="cpu", device_uncond="cpu", cfg_group=cfg_group)
+    return pipe, tags
+
+
+def _fps_run(pipe):
+    noise = torch.randn(1, 21, 16, 8, 12, generator=torch.Generator().manual_seed(3))
+    sent = []
+    pipe.anchor_sink = sent.append
+    _, latents = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
+    return latents, sent
+
+
+def _cfg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pipe, tags = _fps_pipeline(cfg_group=dist.group.WORLD)
+        latents, sent = _fps_run(pipe)
+        q.put((rank, latents, sent[0], sorted(set(tags)), len(tags), pipe.kv_cache_pos is None, pipe.kv_cache_neg is None,
+               pipe.cfg_bytes_exchanged))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_pair_split_world2_gloo():
+    """Two ranks, one per CFG branch, must reproduce the single-process pipeline bit for bit; each rank runs only
+    its branch's forwards and holds only its branch's caches; one flow exchange per denoising step."""
+    pipe, tags = _fps_pipeline()
+    ref_latents, ref_sent = _fps_run(pipe)
+    n_forwards = len(tags)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, latents, anchors, seen, n, pos_none, neg_none, nbytes in res:
+        assert torch.equal(latents, ref_latents), f"rank {rank}: latents differ from the single-process run"
+        assert torch.equal(anchors, ref_sent[0])
+        assert seen == (["pos"] if rank == 0 else ["neg"]) and n == n_forwards // 2
+        assert (pos_none, neg_none) == ((False, True) if rank == 0 else (True, False))
+        # 4 stages x 3 steps, flow of n frames [1, n, 16, 8, 12] fp32 in this CPU test
+        assert nbytes == 3 * (2 + 7 + 6 + 6) * 16 * 8 * 12 * 4
+
+
+def test_lane_placement():
+    # 8 ranks, 2 lanes: 4 segment slots; lane l of slot s is rank 2s + l and hands over to lane l of the next slot
+    assert segments_of_rank(0, 8, 6, lanes=2) == [0, 4] and segments_of_rank(1, 8, 6, lanes=2) == [0, 4]
+    assert segments_of_rank(7, 8, 6, lanes=2) == [3] and segments_of_rank(5, 8, 6, lanes=2) == [2]
+    assert [producer_of(s, 8, 2, 1) for s in range(5)] == [1, 3, 5, 7, 1]

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
     ap.add_argument("--i2v", action="store_true")
+    ap.add_argument("--cfg-pair", action="store_true",
+                    help="CFG-pair split: two ranks per segment (conditional / unconditional branch), world must be even")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -69,11 +71,24 @@ def main():
 
     args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="__negative__",
                                  independent_first_frame=False, sampling_steps=a.sampling_steps, model_kwargs={}, i2v=a.i2v)
-    pipe = CausalFPSInferencePipeline(args, dev, generator=gen, text_encoder=Text(), vae=VAE(), device_cond=dev, device_uncond=dev)
-    channel = AnchorChannel()
-    if world > 1:  # create the NCCL point-to-point connections outside the timed region
+    lanes = 2 if a.cfg_pair else 1
+    cfg_group = None
+    if a.cfg_pair:
+        assert world % 2 == 0, "--cfg-pair needs an even number of ranks"
+        for s in range(world // 2):  # every rank creates every pair group, in the same order
+            grp = dist.new_group([2 * s, 2 * s + 1])
+            if rank // 2 == s:
+                cfg_group = grp
+    torch.manual_seed(1234)  # the pipeline draws its re-noising noise with torch.randn_like: same stream on both lanes
+    pipe = CausalFPSInferencePipeline(args, dev, generator=gen, text_encoder=Text(), vae=VAE(), device_cond=dev, device_uncond=dev,
+                                      cfg_group=cfg_group)
+    channel = AnchorChannel(lanes=lanes)
+    if cfg_group is not None:  # create the pair's communicator outside the timed region
+        warm = [torch.zeros(8, device=dev), torch.zeros(8, device=dev)]
+        dist.all_gather(warm, torch.zeros(8, device=dev), group=cfg_group)
+    if world > lanes:  # create the NCCL point-to-point connections outside the timed region
         buf = torch.zeros(8, device=dev)
-        nxt, prv = (rank + 1) % world, (rank - 1) % world
+        nxt, prv = (rank + lanes) % world, (rank - lanes) % world
         ops = [dist.P2POp(dist.isend, buf, nxt), dist.P2POp(dist.irecv, torch.empty_like(buf), prv)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -113,7 +128,8 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     finite = all(torch.isfinite(v.float()).all().item() for v in outs.values())
     info = dict(rank=rank, segments=sorted(outs), ms=my_ms, launches=model.launch_count(), finite=finite,
-                anchor_bytes_sent=channel.bytes_sent, log=runner.log)
+                anchor_bytes_sent=channel.bytes_sent, cfg_bytes_exchanged=getattr(pipe, "cfg_bytes_exchanged", 0), log=runner.log,
+                checksum={k: float(v.float().abs().sum()) for k, v in outs.items()})
     gathered = [info]
     if world > 1:
         gathered = [None] * world
@@ -124,7 +140,8 @@ def main():
             "value": a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
             "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.segments} segments x 21 latent frames 60x104, "
                                    f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
-                       "parallelism": f"segment-parallel x{world}, anchors over NCCL send/recv"},
+                       "parallelism": (f"segment-parallel x{world // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
+                                       ", anchors over NCCL send/recv")},
             "model_build_s": build_s, "ranks": gathered}))
     if world > 1:
         dist.destroy_process_group()
