@@ -189,8 +189,11 @@ __device__ __forceinline__ void rope_row(uint4 (&v)[NCH], const double2* __restr
   }
 }
 
+// blockIdx.y selects the operand (0 = q, 1 = k, 2 = v), so a warp holds one row of one operand: three times the warps
+// of a row-per-warp layout at a third of the registers, which is what hides the load -> fp64 rotate -> store chain
+// of this single-wave kernel.
 template <int NCH>
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
+__global__ void __launch_bounds__(kRowsPerBlock * 32, NCH <= 8 ? 4 : 1)
 qk_norm_rope_kv_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat16* __restrict__ k_in,
                        const __nv_bfloat16* __restrict__ v_in, int64_t ld_in,
                        const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
@@ -201,57 +204,27 @@ qk_norm_rope_kv_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
   pdl_launch_dependents();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int role = blockIdx.y;
   if (row >= p.S) return;
   const int fs = p.gh * p.gw;
   const int fr = row / fs;
   const int rem = row - fr * fs;
-  const int ph = rem / p.gw;
-  const int pw = rem - ph * p.gw;
-  const int pt = p.frame_pos[fr];
   const int64_t dst_row = static_cast<int64_t>(p.kv_row[fr]) + rem;
-
-  // all three rows are fetched up front (one memory latency instead of three); for the 14B width (NCH = 20) the
-  // registers do not allow it and q, k, v are processed one after the other
-  constexpr bool kTogether = NCH <= 8;
-  uint4 vq[NCH], vk[kTogether ? NCH : 1], vv[kTogether ? NCH : 1];
-  const uint4* rq = reinterpret_cast<const uint4*>(q_in + static_cast<int64_t>(row) * ld_in);
-  const uint4* rk = reinterpret_cast<const uint4*>(k_in + static_cast<int64_t>(row) * ld_in);
-  const uint4* rv = reinterpret_cast<const uint4*>(v_in + static_cast<int64_t>(row) * ld_in);
+  const __nv_bfloat16* src = (role == 0 ? q_in : (role == 1 ? k_in : v_in)) + static_cast<int64_t>(row) * ld_in;
+  __nv_bfloat16* dst = role == 0 ? q_out + static_cast<int64_t>(row) * ldq : (role == 1 ? k_dst : v_dst) + dst_row * ldkv;
+  uint4 v[NCH];
+  const uint4* r = reinterpret_cast<const uint4*>(src);
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) vq[i] = rq[lane + 32 * i];
-  if (kTogether) {
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) vk[i] = rk[lane + 32 * i];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) vv[i] = rv[lane + 32 * i];
+  for (int i = 0; i < NCH; ++i) v[i] = r[lane + 32 * i];
+  if (role < 2) {
+    const int ph = rem / p.gw;
+    const int pw = rem - ph * p.gw;
+    rmsnorm_row<NCH>(v, role == 0 ? wq : wk, lane, p.eps);
+    rope_row<NCH>(v, rope_tab, lane, p.frame_pos[fr], ph, pw);
   }
-  // q
-  {
-    rmsnorm_row<NCH>(vq, wq, lane, p.eps);
-    rope_row<NCH>(vq, rope_tab, lane, pt, ph, pw);
-    uint4* o = reinterpret_cast<uint4*>(q_out + static_cast<int64_t>(row) * ldq);
+  uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = vq[i];
-  }
-  // k
-  {
-    uint4 (&v)[NCH] = *reinterpret_cast<uint4(*)[NCH]>(kTogether ? &vk[0] : &vq[0]);
-    if (!kTogether) {
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) v[i] = rk[lane + 32 * i];
-    }
-    rmsnorm_row<NCH>(v, wk, lane, p.eps);
-    rope_row<NCH>(v, rope_tab, lane, pt, ph, pw);
-    uint4* o = reinterpret_cast<uint4*>(k_dst + dst_row * ldkv);
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = v[i];
-  }
-  // v (plain copy into the cache)
-  {
-    uint4* o = reinterpret_cast<uint4*>(v_dst + dst_row * ldkv);
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = kTogether ? vv[i] : rv[lane + 32 * i];
-  }
+  for (int i = 0; i < NCH; ++i) o[lane + 32 * i] = v[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,7 +476,7 @@ int qk_norm_rope_kv(const void* q_in, const void* k_in, const void* v_in, int64_
     p.kv_row[f] = kv_row[f];
   }
   const int grid = (S + kRowsPerBlock - 1) / kRowsPerBlock;
-  MMPL_DISPATCH_NCH(D, (MMPL_CUDA_LAUNCH(launch_kernel(qk_norm_rope_kv_kernel<NCH>, grid, kRowsPerBlock * 32, 0, st, 
+  MMPL_DISPATCH_NCH(D, (MMPL_CUDA_LAUNCH(launch_kernel(qk_norm_rope_kv_kernel<NCH>, dim3(grid, 3), kRowsPerBlock * 32, 0, st, 
                            static_cast<const __nv_bfloat16*>(q_in), static_cast<const __nv_bfloat16*>(k_in),
                            static_cast<const __nv_bfloat16*>(v_in), ld_in, static_cast<const __nv_bfloat16*>(wq),
                            static_cast<const __nv_bfloat16*>(wk), static_cast<const double2*>(rope_table),
