@@ -405,12 +405,18 @@ constexpr int kPairStageBytes = 2 * kBM * kBK * 2;  // 16 KB A + 16 KB W per CTA
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
 constexpr int kPairBN = 256;
 
-template <int EPI>
+// BN = tile width of the pair: 256, or 224 where that fills the machine better. cfg2's N = 1536 projections are
+// 19 x 6 = 114 tiles of 256 x 256 on 74 pairs (2 waves, the second 54 % full) but 19 x 7 = 133 tiles of 256 x 224
+// (2 waves of tiles that are 12.5 % cheaper); cuBLAS picks the same width for this shape (nvjet 256x224, ncu
+// comparison in profiles/). The smem slots and the TMEM accumulator spacing stay those of BN = 256.
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const GemmParams p) {
   constexpr int ST = kPairStages;
-  constexpr int BN = kPairBN;
+  static_assert(BN % 32 == 0 && BN <= kPairBN && (BN / 2) % 8 == 0, "pair tile width");
+  constexpr uint32_t kTxBytes = 2 * (kBM * kBK * 2 + (BN / 2) * kBK * 2);  // A + W bytes of both CTAs per stage
+  constexpr int kChunksLo = (BN / 32 + 1) / 2;  // 32-column chunks of the left-half epilogue warps; the rest go right
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -472,7 +478,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int row_b = n_blk * BN + static_cast<int>(cta) * (BN / 2);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
-        if (leader) mbar_arrive_expect_tx_elect(&full_bar[s], 2 * kPairStageBytes);
+        if (leader) mbar_arrive_expect_tx_elect(&full_bar[s], kTxBytes);
         tma_load_2d_2cta_elect(smem_a + s * (kPairStageBytes / 2), &map_a, &full_bar[s], kb * kBK, row_a, kEvictNormal);
         tma_load_2d_2cta_elect(smem_b + s * (kPairStageBytes / 2), &map_b, &full_bar[s], kb * kBK, row_b, kEvictLast);
         if (++s == ST) { s = 0; ph ^= 1; }
@@ -481,7 +487,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);  // N = BN columns, half from each CTA's W rows
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -493,7 +499,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * kPairBN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -527,14 +533,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(cta) * kBM + lane_base + lane;
-      constexpr int kChunks = BN / 32 / 2;
       const int half = (warp - 2) >> 2;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN;
+      const int c_begin = half * kChunksLo;
+      const int c_end = c_begin + ((BN / 32) % 2 == 0 ? kChunksLo : (half ? BN / 32 - kChunksLo : kChunksLo));
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * kPairBN;
       if (kb0 > 0) {
         // head segment of this pair's stream-K range: leave the partial accumulator for the tile's owner
         float* dst = p.sk_part + (static_cast<int64_t>(pair) * 2 + cta) * kSlotFloats +
                      static_cast<int64_t>(lane_base + lane) * BN;
-        store_partial_row(taddr, dst, row < p.M, half * kChunks, (half + 1) * kChunks);
+        store_partial_row(taddr, dst, row < p.M, c_begin, c_end);
         __threadfence();
         epi_group_sync();
         if (warp == 2 && lane == 0)
@@ -560,10 +567,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         epi_group_sync();
         const float* part = p.sk_part + (static_cast<int64_t>(pair + 1) * 2 + cta) * kSlotFloats +
                             static_cast<int64_t>(lane_base + lane) * BN;
-        epilogue_tile<BN, EPI>(p, taddr, row, n_blk * BN, half * kChunks, (half + 1) * kChunks, part, q_last - pair,
-                               2 * kSlotFloats);
+        epilogue_tile<BN, EPI>(p, taddr, row, n_blk * BN, c_begin, c_end, part, q_last - pair, 2 * kSlotFloats);
       } else {
-        epilogue_tile<BN, EPI>(p, taddr, row, n_blk * BN, half * kChunks, (half + 1) * kChunks);
+        epilogue_tile<BN, EPI>(p, taddr, row, n_blk * BN, c_begin, c_end);
       }
       tc_fence_before();
       __syncwarp();
@@ -605,16 +611,16 @@ static int ensure_streamk_workspace(int pairs) {
   return MMPL_OK;
 }
 
-template <int EPI>
+template <int BN, int EPI>
 static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
-  auto kern = gemm_bf16_pair_kernel<EPI>;
+  auto kern = gemm_bf16_pair_kernel<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     MMPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
   }
   p.tiles_m = (p.M + 255) / 256;
-  p.tiles_n = (p.N + kPairBN - 1) / kPairBN;
+  p.tiles_n = (p.N + BN - 1) / BN;
   const int tiles = p.tiles_m * p.tiles_n;
   const int max_pairs = sm_count() / 2;
   int pairs = tiles < max_pairs ? tiles : max_pairs;
@@ -624,7 +630,11 @@ static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmPa
   {
     static const int env_gm = getenv("MMPL_GEMM_GROUP_M") ? atoi(getenv("MMPL_GEMM_GROUP_M")) : 0;
     const bool a_fits_l2 = static_cast<int64_t>(p.M) * p.K * 2 <= (32ll << 20);
-    p.group_m = env_gm > 0 ? env_gm : (a_fits_l2 ? p.tiles_m : 8);
+    // A larger than L2's comfortable share: if a whole row of tiles fits in one wave, run whole rows together (each A
+    // panel is then read from HBM once: cfg2's ffn.2 with its 84 MB A read 157 MB with groups of 8 rows, 111 MB is the
+    // minimum); otherwise groups of 8 tile rows.
+    const int rows_per_wave = max_pairs / p.tiles_n;
+    p.group_m = env_gm > 0 ? env_gm : (a_fits_l2 ? p.tiles_m : (rows_per_wave >= 2 ? rows_per_wave : 8));
     if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
   }
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -645,16 +655,31 @@ static int launch_gemm_pair(const CUtensorMap* ma, const CUtensorMap* mb, GemmPa
   return MMPL_OK;
 }
 
+template <int BN>
 static int dispatch_epi_pair(int epi, const CUtensorMap* ma, const CUtensorMap* mb, const GemmParams& p,
                              cudaStream_t stream) {
   switch (epi) {
-    case MMPL_EPI_BIAS: return launch_gemm_pair<MMPL_EPI_BIAS>(ma, mb, p, stream);
-    case MMPL_EPI_BIAS_GELU: return launch_gemm_pair<MMPL_EPI_BIAS_GELU>(ma, mb, p, stream);
-    case MMPL_EPI_BIAS_SILU: return launch_gemm_pair<MMPL_EPI_BIAS_SILU>(ma, mb, p, stream);
-    case MMPL_EPI_BIAS_RES: return launch_gemm_pair<MMPL_EPI_BIAS_RES>(ma, mb, p, stream);
-    case MMPL_EPI_BIAS_GATE_RES: return launch_gemm_pair<MMPL_EPI_BIAS_GATE_RES>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS: return launch_gemm_pair<BN, MMPL_EPI_BIAS>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GELU: return launch_gemm_pair<BN, MMPL_EPI_BIAS_GELU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_SILU: return launch_gemm_pair<BN, MMPL_EPI_BIAS_SILU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_RES: return launch_gemm_pair<BN, MMPL_EPI_BIAS_RES>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GATE_RES: return launch_gemm_pair<BN, MMPL_EPI_BIAS_GATE_RES>(ma, mb, p, stream);
     default: set_error("gemm: unknown epilogue %d", epi); return MMPL_ERR_ARG;
   }
+}
+
+// Width of the pair tile: the candidate with the lowest (waves x tile width), i.e. the shortest main loop per pair.
+static int pick_pair_bn(int M, int N) {
+  const int pairs = (sm_count() > 0 ? sm_count() : 148) / 2;
+  const int tiles_m = (M + 255) / 256;
+  int best_bn = 256;
+  long long best = -1;
+  for (int bn : {256, 224}) {
+    const int tiles = tiles_m * ((N + bn - 1) / bn);
+    const long long cost = static_cast<long long>((tiles + pairs - 1) / pairs) * bn;
+    if (best < 0 || cost < best) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
 }
 
 template <int BN, int EPI>
@@ -717,8 +742,8 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   if (epilogue == MMPL_EPI_BIAS_GATE_RES)
     MMPL_CHECK(gate != nullptr && rows_per_frame > 0 && gate_stride % 8 == 0, MMPL_ERR_ARG,
                "gemm: gate epilogue needs gate, rows_per_frame > 0 and gate_stride %% 8 == 0");
-  // tile_n 512 selects the cta_group::2 kernel (256 x 256 tile per CTA pair); auto-selected for large problems
-  bool use_pair = force_bn == 512 || (force_bn == 0 && N % 256 == 0 && M >= 512);
+  // tile_n 512 / 448 select the cta_group::2 kernel (256 x 256 / 256 x 224 tile per CTA pair); auto-selected for large problems
+  bool use_pair = force_bn == 512 || force_bn == 448 || (force_bn == 0 && N % 256 == 0 && M >= 512);
   if (use_pair && force_bn == 0 && K <= 2048) {
     // Short-K problems whose 256 x 256 tiles leave the last wave mostly empty while 128 x 128 tiles fill theirs:
     // cfg2's o / cross-attention projections (M = 4680, N = K = 1536) are 114 pair tiles on 74 pairs (1.54 waves) but
@@ -734,8 +759,10 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   }
   if (use_pair) {
     MMPL_CHECK(N % 8 == 0, MMPL_ERR_SHAPE, "gemm: N must be a multiple of 8");
+    static const int env_bn = getenv("MMPL_GEMM_PAIR_BN") ? atoi(getenv("MMPL_GEMM_PAIR_BN")) : 0;
+    const int pbn = force_bn == 448 ? 224 : (force_bn == 512 ? 256 : (env_bn == 224 || env_bn == 256 ? env_bn : pick_pair_bn(M, N)));
     const CUtensorMap* pa = get_tensor_map_bf16(a, M, K, lda, kBM);
-    const CUtensorMap* pb = get_tensor_map_bf16(w, N, K, ldw, kBM);
+    const CUtensorMap* pb = get_tensor_map_bf16(w, N, K, ldw, pbn / 2);  // each CTA loads half of the tile's W rows
     if (!pa || !pb) return MMPL_ERR_CUDA;
     GemmParams pp{};
     pp.M = M; pp.N = N; pp.K = K;
@@ -747,7 +774,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     pp.gate = static_cast<const __nv_bfloat16*>(gate);
     pp.gate_stride = gate_stride;
     pp.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
-    return dispatch_epi_pair(epilogue, pa, pb, pp, stream);
+    return pbn == 224 ? dispatch_epi_pair<224>(epilogue, pa, pb, pp, stream) : dispatch_epi_pair<256>(epilogue, pa, pb, pp, stream);
   }
   const int bn = force_bn ? force_bn : pick_bn(M, N);
   MMPL_CHECK(bn == 64 || bn == 128 || bn == 256, MMPL_ERR_ARG, "gemm: tile width %d not supported", bn);

@@ -45,6 +45,9 @@ def _report(name, got, ref, atol, rtol, outlier_frac=0.0, outlier_abs=0.0):
     # tile 512 = the cta_group::2 kernel (256 x 256 per CTA pair); 256 = force the single-CTA kernel
     (256, 256, 64, 512), (300, 512, 192, 512), (4680, 1536, 1536, 512), (4680, 4608, 1536, 512), (4680, 8960, 1536, 512),
     (4680, 1536, 8960, 512), (10920, 5120, 5120, 512), (4680, 1536, 1536, 256), (4680, 1536, 1536, 128),
+    # tile 448 = the cta_group::2 kernel with 256 x 224 tiles (N tail: 1536 = 6 x 224 + 192, 512 = 2 x 224 + 64)
+    (256, 224, 64, 448), (300, 512, 192, 448), (4680, 1536, 1536, 448), (4680, 1536, 8960, 448), (4680, 4608, 1536, 448),
+    (1170, 1536, 1536, 448), (10920, 5120, 5120, 448),
 ])
 def test_gemm_bias(M, N, K, tile):
     ops = _ops()
@@ -53,7 +56,8 @@ def test_gemm_bias(M, N, K, tile):
     _report(f"gemm {M}x{N}x{K} tile={tile}", got, O.linear(x, w, b), atol=2e-2, rtol=2e-2)
 
 
-@pytest.mark.parametrize("M,N,K,tile", [(1170, 1536, 1536, 0), (4680, 1536, 1536, 0), (4680, 1536, 1536, 128), (1170, 1536, 1536, 512)])
+@pytest.mark.parametrize("M,N,K,tile", [(1170, 1536, 1536, 0), (4680, 1536, 1536, 0), (4680, 1536, 1536, 128), (1170, 1536, 1536, 512),
+                                        (4680, 1536, 1536, 448), (4680, 1536, 8960, 0), (1170, 1536, 1536, 448)])
 def test_gemm_epilogues(M, N, K, tile):
     import functools
     ops = _ops()
@@ -75,9 +79,10 @@ def test_gemm_epilogues(M, N, K, tile):
     _report("gate_res_inplace", xres, ref, 4e-2, 2e-2)
 
 
-@pytest.mark.parametrize("M,N,K", [(4680, 1536, 1536), (4680, 1536, 8960), (4680, 4608, 1536), (10920, 5120, 5120),
-                                   (1170, 1536, 1536), (300, 512, 1024), (1998, 1280, 512)])
-def test_gemm_streamk_schedule(M, N, K):
+@pytest.mark.parametrize("M,N,K,tile", [(4680, 1536, 1536, 512), (4680, 1536, 8960, 512), (4680, 4608, 1536, 512),
+                                        (10920, 5120, 5120, 512), (1170, 1536, 1536, 512), (300, 512, 1024, 512),
+                                        (1998, 1280, 512, 512), (4680, 1536, 8960, 448), (1170, 1536, 1536, 448)])
+def test_gemm_streamk_schedule(M, N, K, tile):
     """The stream-K tail schedule of the cta_group::2 kernel (gemm_tcgen05.cu: PairSched) against the whole-tile
     schedule and the oracle: forced on (mode 1) for shapes of 1 ... 12 waves incl. fewer tiles than CTA pairs; repeated
     launches and a CUDA-graph replay check that the hand-over flags are re-armed; results must be deterministic."""
@@ -90,17 +95,17 @@ def test_gemm_streamk_schedule(M, N, K):
     ref_gr = O.gate_residual(res, ref, gate, fs)
     try:
         lib.mmpl_gemm_set_streamk(0)
-        dp = ops.linear(x, w, b, tile_n=512)
+        dp = ops.linear(x, w, b, tile_n=tile)
         lib.mmpl_gemm_set_streamk(1)
-        outs = [ops.linear(x, w, b, tile_n=512) for _ in range(3)]
-        gr = ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GATE_RES, residual=res, gate=gate, rows_per_frame=fs, tile_n=512)
-        gelu = ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GELU, tile_n=512)
+        outs = [ops.linear(x, w, b, tile_n=tile) for _ in range(3)]
+        gr = ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GATE_RES, residual=res, gate=gate, rows_per_frame=fs, tile_n=tile)
+        gelu = ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GELU, tile_n=tile)
         out_g = torch.empty_like(outs[0])
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            ops.linear(x, w, b, out=out_g, tile_n=512)
-            ops.linear(x, w, b, out=out_g, tile_n=512)
+            ops.linear(x, w, b, out=out_g, tile_n=tile)
+            ops.linear(x, w, b, out=out_g, tile_n=tile)
         for _ in range(3):
             out_g.zero_()
             graph.replay()

@@ -61,6 +61,8 @@ def bench_gemm(shapes, tiles):
         for t in tiles:
             if t in (128, 256) and N % t:
                 continue
+            if t == 0 and os.environ.get('GEMM_NO_AUTO'):
+                continue
             i = [0]
 
             def run():
@@ -96,6 +98,15 @@ def bench_attn(cases):
             line += f" split{sp}: {ms * 1e3:7.1f} us {4 * Lq * Lk * H * 128 / ms / 1e9:6.1f} |"
             print(f"  [{Lq}x{Lk}x{H}] split{sp}: {ms * 1e3:7.1f} us", flush=True)
         lib.mmpl_attn_set_split(0)
+        if os.environ.get("ATTN_CUDNN", "1") != "0":  # cuDNN's Blackwell fused attention through torch SDPA, as a yardstick
+            try:
+                from torch.nn.attention import SDPBackend, sdpa_kernel
+                q4, k4, v4 = (t.transpose(0, 1)[None] for t in (q, k, v))  # [1, H, L, 128] views
+                with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+                    ms3 = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4), iters=10)
+                line += f" | cuDNN SDPA: {ms3 * 1e3:8.1f} us {4 * Lq * Lk * H * 128 / ms3 / 1e9:7.1f} TF/s"
+            except Exception as e:  # noqa: BLE001
+                line += f" | cuDNN SDPA unavailable ({type(e).__name__}: {str(e)[:80]})"
         if os.environ.get("ATTN_NO_FA2"):
             print(line, flush=True)
             continue
@@ -115,7 +126,7 @@ if __name__ == "__main__":
     if "gemm" in a.what:
         bench_gemm([(4680, 4608, 1536), (4680, 1536, 1536), (4680, 8960, 1536), (4680, 1536, 8960),
                     (10920, 15360, 5120), (10920, 5120, 5120), (10920, 13824, 5120), (10920, 5120, 13824)],
-                   tiles=[128, 256, 512])
+                   tiles=[int(t) for t in os.environ.get('GEMM_TILES', '128,256,512').split(',')])
     if "attn" in a.what:
         shapes = [(4680, 4680, 12), (4680, 18720, 12), (4680, 32760, 12), (4680, 512, 12), (10920, 14040, 40)]
         if os.environ.get("ATTN_SHAPES"):  # e.g. "4680x9360x12,4680x14040x12"
