@@ -123,15 +123,15 @@ struct Piece { int head, q_row0, t0, n, slot; bool whole; };
 //    of a partial piece is (group, CTA, piece starts its CTA's range ? 0 : 1), so 2*G slots per group suffice.
 struct RangeGroup {
   int heads, units;     // heads and units in this group
-  long long W;          // KV-tile units in this group = units * T
+  int W;                // KV-tile units in this group = units * T  (host guarantees W * (G + 1) < 2^31)
   __device__ __forceinline__ void set(const AttnParams& p, int g) {
     heads = min(p.hg, p.H - g * p.hg);
     units = heads * p.QP;
-    W = static_cast<long long>(units) * p.T;
+    W = units * p.T;
   }
-  __device__ __forceinline__ long long lo(int c, int G) const { return c * W / G; }
+  __device__ __forceinline__ int lo(int c, int G) const { return c * W / G; }
   // the CTA whose range contains position x: largest c with lo(c) <= x
-  __device__ __forceinline__ int cta_of(long long x, int G) const { return static_cast<int>(((x + 1) * G + W - 1) / W) - 1; }
+  __device__ __forceinline__ int cta_of(int x, int G) const { return ((x + 1) * G + W - 1) / W - 1; }
 };
 
 struct PieceIter {
@@ -140,7 +140,7 @@ struct PieceIter {
   int pi;
   // ranges
   int g, ngroups;
-  long long pos, lo, hi;
+  int pos, lo, hi;
   RangeGroup grp;
   __device__ __forceinline__ void init(const AttnParams& p, int cta, int grid) {
     G = grid;
@@ -159,8 +159,8 @@ struct PieceIter {
       const int chunk = r / p.QP;
       const int qp = r - chunk * p.QP;
       pc.q_row0 = qp * (2 * kQTile);
-      pc.t0 = static_cast<int>(static_cast<long long>(chunk) * p.T / p.split);
-      pc.n = static_cast<int>(static_cast<long long>(chunk + 1) * p.T / p.split) - pc.t0;
+      pc.t0 = chunk * p.T / p.split;
+      pc.n = (chunk + 1) * p.T / p.split - pc.t0;
       pc.slot = (pc.head * p.QP + qp) * p.split + chunk;
       pc.whole = p.split == 1;
       pi += G;
@@ -172,13 +172,13 @@ struct PieceIter {
       lo = pos = grp.lo(c, G);
       hi = grp.lo(c + 1, G);
     }
-    const int ul = static_cast<int>(pos / p.T);
+    const int ul = pos / p.T;
     const int head_l = ul / p.QP;
     pc.head = g * p.hg + head_l;
     pc.q_row0 = (ul - head_l * p.QP) * (2 * kQTile);
-    pc.t0 = static_cast<int>(pos - static_cast<long long>(ul) * p.T);
-    const long long end = min(hi, static_cast<long long>(ul + 1) * p.T);
-    pc.n = static_cast<int>(end - pos);
+    pc.t0 = pos - ul * p.T;
+    const int end = min(hi, (ul + 1) * p.T);
+    pc.n = end - pos;
     pc.whole = pc.n == p.T;
     pc.slot = (g * G + c) * 2 + (pos == lo ? 0 : 1);
     pos = end;
@@ -619,14 +619,14 @@ attn_combine_kernel(const AttnParams p) {
   const int q_row = (u - head * p.QP) * kUnitRows + row_in_unit;
   // piece i of the unit -> workspace slot, or -1 (range schedule: a CTA whose range is empty holds no piece)
   int np, c_first = 0, g = 0;
-  long long start = 0;
+  int start = 0;
   RangeGroup grp;
   if (p.hg == 0) {
     np = p.split;
   } else {
     g = head / p.hg;
     grp.set(p, g);
-    start = static_cast<long long>(u - g * p.hg * p.QP) * p.T;
+    start = (u - g * p.hg * p.QP) * p.T;
     c_first = grp.cta_of(start, p.G);
     np = grp.cta_of(start + p.T - 1, p.G) - c_first + 1;
     if (np == 1) return;  // written directly by the CTA that ran the whole unit
@@ -635,7 +635,7 @@ attn_combine_kernel(const AttnParams p) {
   auto slot_of = [&](int i) -> int {
     if (p.hg == 0) return u * p.split + i;
     const int c = c_first + i;
-    const long long lo = grp.lo(c, p.G);
+    const int lo = grp.lo(c, p.G);
     if (grp.lo(c + 1, p.G) <= lo) return -1;
     return (g * p.G + c) * 2 + (max(lo, start) == lo ? 0 : 1);  // same rule as PieceIter: does the piece open its CTA's range?
   };
@@ -729,13 +729,15 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
     const double kv_mb = static_cast<double>(H) * T * kKVTile * 512.0 / (1 << 20);
     const double pieces_per_cta = static_cast<double>(U) / sms + 1.0;
     const double cost_ranges = static_cast<double>(U) * T / sms + piece_fixed * pieces_per_cta + merge_fixed + merge_per_piece * 2.0 * sms;
-    const bool possible = T >= 16 && static_cast<long long>(U) * T >= 8ll * sms && kv_mb <= l2_mb;
+    const bool fits32 = static_cast<long long>(U) * T * (sms + 1) < (1ll << 31);  // PieceIter's range arithmetic is 32-bit
+    const bool possible = T >= 16 && static_cast<long long>(U) * T >= 8ll * sms && kv_mb <= l2_mb && fits32;
     if (possible && (mode_env == 1 || (mode_env < 0 && cost_ranges < best))) hg = H;
   }
   if (force_split > 0 && force_split <= T) {
     best_split = force_split;
     hg = 0;
-  } else if (force_split < 0 && T >= 2 && static_cast<long long>(U) * T >= 2ll * sms) {
+  } else if (force_split < 0 && T >= 2 && static_cast<long long>(U) * T >= 2ll * sms &&
+             static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
     hg = -force_split < H ? -force_split : H;  // test hook: range schedule with this many heads per group
   }
   static const bool nonpersistent = getenv("MMPL_ATTN_NONPERSISTENT") != nullptr;
