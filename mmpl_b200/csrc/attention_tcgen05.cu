@@ -639,6 +639,8 @@ attn_combine_kernel(const AttnParams p) {
     if (grp.lo(c + 1, p.G) <= lo) return -1;
     return (g * p.G + c) * 2 + (max(lo, start) == lo ? 0 : 1);  // same rule as PieceIter: does the piece open its CTA's range?
   };
+  // pieces are taken four at a time with all their loads issued before the first use: the kernel is a single pass over
+  // ~90 MB of partials that have mostly left L2, i.e. bound by how many loads are in flight
   float M = -INFINITY;
   for (int i = 0; i < np; ++i) {
     const int sl = slot_of(i);
@@ -646,15 +648,26 @@ attn_combine_kernel(const AttnParams p) {
   }
   float L = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = 0; i < np; ++i) {
-    const int sl = slot_of(i);
-    if (sl < 0) continue;
-    const int64_t r = static_cast<int64_t>(sl) * kUnitRows + row_in_unit;
-    const float2 ml = *reinterpret_cast<const float2*>(p.part_ml + r * 2);
-    const float w = exp2f(ml.x - M);
-    L += w * ml.y;
-    const float4 o = *reinterpret_cast<const float4*>(p.part_o + r * kHD + lane * 4);
-    acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+  for (int i0 = 0; i0 < np; i0 += 4) {
+    float2 ml[4];
+    float4 o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int sl = i0 + k < np ? slot_of(i0 + k) : -1;
+      ml[k] = make_float2(-INFINITY, 0.f);
+      o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sl >= 0) {
+        const int64_t r = static_cast<int64_t>(sl) * kUnitRows + row_in_unit;
+        ml[k] = *reinterpret_cast<const float2*>(p.part_ml + r * 2);
+        o[k] = *reinterpret_cast<const float4*>(p.part_o + r * kHD + lane * 4);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float w = exp2f(ml[k].x - M);  // 0 for the slots that are not there
+      L += w * ml[k].y;
+      acc.x += w * o[k].x; acc.y += w * o[k].y; acc.z += w * o[k].z; acc.w += w * o[k].w;
+    }
   }
   const float inv = 1.0f / L;
   uint2 w2 = make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
