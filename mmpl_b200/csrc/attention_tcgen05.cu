@@ -105,7 +105,10 @@ struct AttnParams {
   int seg_src[kMaxSeg];
   // range schedule (PieceIter): heads are taken in groups of `hg`; 0 = uniform-split schedule
   int hg;
-  int G;          // CTAs of flash_attn_kernel (attn_combine_kernel needs it to locate the pieces of a unit)
+  int G;          // CTAs of flash_attn_kernel (needed to locate the pieces of a unit when merging)
+  // merge of partial pieces inside flash_attn_kernel: per (unit, query tile) arrival counters (zero between launches),
+  // nullptr = leave the merge to attn_combine_kernel
+  int* merge_cnt;
 };
 
 // A piece = KV tiles [t0, t0 + n) of one unit. `whole`: the piece is the entire unit and writes the normalised bf16
@@ -186,6 +189,40 @@ struct PieceIter {
   }
 };
 
+// The pieces a unit was cut into: uniform split -> slots u*split + i; range schedule -> one per CTA whose range
+// overlaps the unit (same arithmetic as PieceIter; a CTA whose range is empty holds none: slot() = -1).
+struct UnitPieces {
+  int np, u, c_first, g, start;
+  RangeGroup grp;
+  __device__ __forceinline__ void init(const AttnParams& p, int unit) {
+    u = unit;
+    c_first = g = start = 0;
+    if (p.hg == 0) {
+      np = p.split;
+    } else {
+      g = (u / p.QP) / p.hg;
+      grp.set(p, g);
+      start = (u - g * p.hg * p.QP) * p.T;
+      c_first = grp.cta_of(start, p.G);
+      np = grp.cta_of(start + p.T - 1, p.G) - c_first + 1;
+    }
+  }
+  __device__ __forceinline__ int slot(const AttnParams& p, int i) const {
+    if (p.hg == 0) return u * p.split + i;
+    const int c = c_first + i;
+    const int lo = grp.lo(c, p.G);
+    if (grp.lo(c + 1, p.G) <= lo) return -1;
+    return (g * p.G + c) * 2 + (max(lo, start) == lo ? 0 : 1);  // does the piece open its CTA's range?
+  }
+  // pieces that really exist (the arrival count that makes a piece the last one)
+  __device__ __forceinline__ int count(const AttnParams& p) const {
+    if (p.hg == 0) return np;
+    int n = 0;
+    for (int i = 0; i < np; ++i) n += slot(p, i) >= 0 ? 1 : 0;
+    return n;
+  }
+};
+
 // Select over the (at most 8) segment parameters without indexing the kernel-parameter arrays dynamically
 // (a dynamic index would make the compiler copy them to local memory).
 __device__ __forceinline__ int seg_field(const int (&a)[kMaxSeg], int i) {
@@ -248,6 +285,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint64_t* o_full = bars + 16;            // 1
   uint64_t* o_empty = bars + 17;           // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  int* merge_ticket = reinterpret_cast<int*>(bars + 20);  // [query tile]: arrival ticket of the current partial piece
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -588,6 +626,59 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[qt]);
+      if (!pc.whole && p.merge_cnt != nullptr) {
+        // Merge inside the kernel: the piece of a unit that finishes last adds up all of them (its own included, read
+        // back from L2 like the others) and writes the bf16 output, so the partials never make the round trip through
+        // HBM that a separate merge kernel pays (ncu: 88 MB read back, 35 us per launch at L_kv >= 18720).
+        // Per query tile: this warpgroup's 128 rows are fenced and counted independently of the other one.
+        const int u = head * p.QP + pc.q_row0 / kUnitRows;
+        UnitPieces up;
+        up.init(p, u);
+        __threadfence();
+        auto wg_sync = [&]() {  // the four softmax warps of this query tile
+          if (qt == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+        };
+        wg_sync();
+        if ((warp & 3) == 0 && lane == 0) merge_ticket[qt] = atomicAdd(p.merge_cnt + 2 * u + qt, 1);
+        wg_sync();
+        if (merge_ticket[qt] == up.count(p) - 1) {
+          __threadfence();
+          if ((warp & 3) == 0 && lane == 0) p.merge_cnt[2 * u + qt] = 0;  // re-armed for the next launch
+          float M = -INFINITY;
+          for (int i = 0; i < up.np; ++i) {
+            const int sl = up.slot(p, i);
+            if (sl >= 0) M = fmaxf(M, __ldcg(p.part_ml + (static_cast<int64_t>(sl) * kUnitRows + row_in_unit) * 2));
+          }
+          float L = 0.f;
+          float acc[kHD];
+#pragma unroll
+          for (int c = 0; c < kHD; ++c) acc[c] = 0.f;
+          for (int i = 0; i < up.np; ++i) {
+            const int sl = up.slot(p, i);
+            if (sl < 0) continue;
+            const int64_t r = static_cast<int64_t>(sl) * kUnitRows + row_in_unit;
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + r * 2));
+            const float w = exp2f(ml.x - M);
+            L += w * ml.y;
+            const float4* src = reinterpret_cast<const float4*>(p.part_o + r * kHD);
+#pragma unroll
+            for (int c = 0; c < kHD / 4; ++c) {
+              const float4 v = __ldcg(src + c);
+              acc[4 * c] += w * v.x; acc[4 * c + 1] += w * v.y; acc[4 * c + 2] += w * v.z; acc[4 * c + 3] += w * v.w;
+            }
+          }
+          if (q_row < p.Lq) {
+            const float inv = 1.0f / L;
+            __nv_bfloat16* orow = p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD;
+#pragma unroll
+            for (int c = 0; c < kHD / 8; ++c)
+              *reinterpret_cast<uint4*>(orow + c * 8) =
+                  make_uint4(pack_bf16x2(acc[8 * c] * inv, acc[8 * c + 1] * inv), pack_bf16x2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv),
+                             pack_bf16x2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv), pack_bf16x2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv));
+          }
+        }
+      }
       g += n;
     }
 #if MMPL_ATTN_TIMING
@@ -617,28 +708,12 @@ attn_combine_kernel(const AttnParams p) {
   const int lane = threadIdx.x & 31;
   const int head = u / p.QP;
   const int q_row = (u - head * p.QP) * kUnitRows + row_in_unit;
-  // piece i of the unit -> workspace slot, or -1 (range schedule: a CTA whose range is empty holds no piece)
-  int np, c_first = 0, g = 0;
-  int start = 0;
-  RangeGroup grp;
-  if (p.hg == 0) {
-    np = p.split;
-  } else {
-    g = head / p.hg;
-    grp.set(p, g);
-    start = (u - g * p.hg * p.QP) * p.T;
-    c_first = grp.cta_of(start, p.G);
-    np = grp.cta_of(start + p.T - 1, p.G) - c_first + 1;
-    if (np == 1) return;  // written directly by the CTA that ran the whole unit
-  }
+  UnitPieces up;
+  up.init(p, u);
+  const int np = up.np;
+  if (p.hg != 0 && np == 1) return;  // written directly by the CTA that ran the whole unit
   if (q_row >= p.Lq) return;
-  auto slot_of = [&](int i) -> int {
-    if (p.hg == 0) return u * p.split + i;
-    const int c = c_first + i;
-    const int lo = grp.lo(c, p.G);
-    if (grp.lo(c + 1, p.G) <= lo) return -1;
-    return (g * p.G + c) * 2 + (max(lo, start) == lo ? 0 : 1);  // same rule as PieceIter: does the piece open its CTA's range?
-  };
+  auto slot_of = [&](int i) -> int { return up.slot(p, i); };
   // pieces are taken four at a time with all their loads issued before the first use: the kernel is a single pass over
   // ~90 MB of partials that have mostly left L2, i.e. bound by how many loads are in flight
   float M = -INFINITY;
@@ -674,9 +749,12 @@ attn_combine_kernel(const AttnParams p) {
   *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD + lane * 4) = w2;
 }
 
-// Workspace for partial pieces (grown on demand; one per process, used by launches on one stream at a time).
+// Workspace for partial pieces (grown on demand; one per process, used by launches on one stream at a time) and the
+// arrival counters of the in-kernel merge (zero between launches: the last piece of a unit clears its counter).
 static float* g_part = nullptr;
 static size_t g_part_bytes = 0;
+static int* g_merge_cnt = nullptr;
+static size_t g_merge_cnt_n = 0;
 int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
                     int64_t ldkv0, int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1,
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
@@ -781,6 +859,25 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
     }
     p.part_o = g_part;
     p.part_ml = g_part + slots * kUnitRows * kHD;
+    // Who merges the partial pieces. Range schedule: the pieces of a unit run on neighbouring CTAs at the same time, the
+    // last one to finish merges them inside the kernel while they are still in L2 (3.5 % faster than the merge kernel
+    // at L_kv = 9360 / 14040). Uniform split: the chunks of a unit run rounds apart, the partials have left L2 by the
+    // time the last chunk is done and the in-kernel merge stalls that CTA's softmax warps on HBM reads (10-25 % slower
+    // at L_kv >= 18720): attn_combine_kernel. MMPL_ATTN_MERGE=inline|kernel forces one for both (tests, A/B).
+    static const char* merge_env = getenv("MMPL_ATTN_MERGE");
+    const bool merge_in_kernel = merge_env ? merge_env[0] == 'i' : hg > 0;
+    if (merge_in_kernel) {
+      const size_t need_cnt = static_cast<size_t>(U) * 2;
+      if (need_cnt > g_merge_cnt_n) {
+        if (g_merge_cnt) MMPL_CUDA(cudaFree(g_merge_cnt));
+        g_merge_cnt = nullptr;
+        g_merge_cnt_n = 0;
+        MMPL_CUDA(cudaMalloc(&g_merge_cnt, need_cnt * sizeof(int)));
+        MMPL_CUDA(cudaMemset(g_merge_cnt, 0, need_cnt * sizeof(int)));
+        g_merge_cnt_n = need_cnt;
+      }
+      p.merge_cnt = g_merge_cnt;
+    }
   }
 
   static bool attr_set = false;
@@ -790,7 +887,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   }
   MMPL_CUDA_LAUNCH(launch_kernel(flash_attn_kernel, G, kAttnThreads, kAttnSmem, stream, *mq, *mk0, *mv0, *mk1, *mv1, p));
   MMPL_CUDA(cudaGetLastError());
-  if (slots > 0) {
+  if (slots > 0 && p.merge_cnt == nullptr) {
     MMPL_CUDA_LAUNCH(launch_kernel(attn_combine_kernel, U * 32, 256, 0, stream, p));
     MMPL_CUDA(cudaGetLastError());
   }

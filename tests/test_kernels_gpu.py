@@ -190,6 +190,33 @@ def test_flash_attn_range_schedule(Lq, Lk, H, hg):
     _report("ranges over segments", got_seg, O.attention(q, k[idx], v[idx]), atol=1e-2, rtol=2e-2)
 
 
+def test_flash_attn_merge_kernel_fallback():
+    """Partial pieces are merged inside flash_attn_kernel (default for the range schedule) or by attn_combine_kernel
+    (default for the uniform split); MMPL_ATTN_MERGE=inline|kernel forces one for both schedules (read once per process,
+    hence the subprocess). Both must give the same result for both schedules."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from mmpl_b200 import ops, _lib\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "q, k, v = (torch.randn(n, 3, 128, generator=g).to(torch.bfloat16).cuda() for n in (700, 5000, 5000))\n"
+        "lib = _lib.load(); outs = []\n"
+        "for sp in (3, -3):\n"
+        "    lib.mmpl_attn_set_split(sp); outs.append(ops.flash_attn(q, k, v).float().cpu())\n"
+        "torch.save(outs, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for mode in ("inline", "kernel"):
+        path = f"/tmp/mmpl_merge_{mode}_{os.getpid()}.pt"
+        env = dict(os.environ, MMPL_ATTN_MERGE=mode)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        res[mode] = torch.load(path)
+        os.remove(path)
+    for a, b in zip(res["inline"], res["kernel"]):
+        assert torch.isfinite(a).all() and (a - b).abs().max().item() <= 1e-2, "in-kernel merge and attn_combine_kernel disagree"
+
+
 def test_flash_attn_large_logits():
     """Rows whose running max grows a lot between KV tiles exercise the lazy O rescale."""
     ops = _ops()
