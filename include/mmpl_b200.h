@@ -67,8 +67,12 @@ int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                     int64_t ldo, float softmax_scale, void* stream);
 
 /* Tuning / test hook for the attention work partition: split > 0 forces the uniform schedule with that many KV chunks
- * per unit; split < 0 forces the range schedule with -split heads per group; 0 = cost model (default). */
+ * per unit; -1000 < split < 0 forces the range schedule with -split heads per group; split <= -1000 forces the hybrid
+ * schedule (whole units in lockstep rounds, the remainder as ranges) wherever it applies; 0 = cost model (default). */
 int mmpl_attn_set_split(int split);
+/* Test hook: run the persistent attention grid with `ctas` CTAs instead of one per SM (0 = default), so that small
+ * problems exercise the multi-round schedules. */
+int mmpl_attn_set_ctas(int ctas);
 /* Tuning / test hook: stream-K tail schedule of the cta_group::2 GEMM: 0 = never (default; slower on B200 at the
  * cfg2 shapes, see gemm_tcgen05.cu), -1 = automatic (when whole 256x256 tiles would leave more than 4 % of the last
  * wave empty), 1 = whenever tiles % pairs != 0. */

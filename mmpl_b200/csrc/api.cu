@@ -140,6 +140,11 @@ int mmpl_attn_set_split(int split) {
   return MMPL_OK;
 }
 
+int mmpl_attn_set_ctas(int ctas) {
+  flash_attn_force_ctas(ctas);
+  return MMPL_OK;
+}
+
 int mmpl_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                      const void* scale, int64_t mod_stride, int rows_per_frame, void* stream) {
   COUNTED(ln_modulate(x, ldx, out, ldo, S, D, eps, shift, scale, mod_stride, rows_per_frame,

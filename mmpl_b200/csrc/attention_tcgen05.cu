@@ -37,6 +37,15 @@
 #ifndef MMPL_ATTN_HALVES
 #define MMPL_ATTN_HALVES 1
 #endif
+// 0 (namespace prod): S of a KV tile is handed to the softmax warps whole. 1 (namespace half, compiled by
+// attention_tcgen05_half.cu): S is produced, exponentiated and consumed in two independent 64-column halves, which
+// shortens the S -> P -> P.V -> next S round trip. Measured on B200 (profiles/r01_microbench_attention_halftile.txt):
+// the half-tile pipeline is 22 % faster for the 4-tile cross-attention (23.6 vs 30.2 us) and 0-6 % slower for the
+// long self-attention ranges (twice the barriers, fences and N=64 MMAs per tile), so the dispatcher
+// (attention_dispatch.cu) uses it for short KV ranges only.
+#ifndef MMPL_ATTN_SPLIT_S
+#define MMPL_ATTN_SPLIT_S 0
+#endif
 
 #ifndef MMPL_ATTN_TIMING
 #define MMPL_ATTN_TIMING 0
@@ -106,6 +115,9 @@ struct AttnParams {
   // range schedule (PieceIter): heads are taken in groups of `hg`; 0 = uniform-split schedule
   int hg;
   int G;          // CTAs of flash_attn_kernel (needed to locate the pieces of a unit when merging)
+  // hybrid schedule (hg == H): units [0, u_base) run whole, CTA c takes units c, c+G, ... (u_base = rounds * G); only
+  // the remaining units [u_base, U) are cut into ranges
+  int u_base;
   // merge of partial pieces inside flash_attn_kernel: per (unit, query tile) arrival counters (zero between launches),
   // nullptr = leave the merge to attn_combine_kernel
   int* merge_cnt;
@@ -124,12 +136,20 @@ struct Piece { int head, q_row0, t0, n, slot; bool whole; };
 //    units each, which whole units or equal chunks can only approximate), and a CTA starts 2-3 pieces per group
 //    instead of one per chunk. A unit that straddles a range boundary is merged by attn_combine_kernel; the slot
 //    of a partial piece is (group, CTA, piece starts its CTA's range ? 0 : 1), so 2*G slots per group suffice.
+//  * hybrid (hg == H, u_base > 0): U units on G CTAs is U/G = r + f units each. The first r*G units run whole, one per
+//    CTA and round, neighbouring CTAs on the same head streaming its K/V in lockstep from tile 0 (the uniform
+//    schedule's L2 sharing, no partials); only the last f*G units go through the range schedule, so every CTA still
+//    gets the same number of KV tiles, the partials are few (2 per CTA) and merged in the kernel while L2-hot, and the
+//    K/V the free-running CTAs of that phase touch is f*G/QP heads' worth instead of all of it (cfg2: 228 units =
+//    148 whole + 80 ranged over 5 heads).
 struct RangeGroup {
-  int heads, units;     // heads and units in this group
+  int heads, units;     // heads and units in this group (units: only those the range schedule covers)
+  int first_unit;       // global index of the group's first ranged unit
   int W;                // KV-tile units in this group = units * T  (host guarantees W * (G + 1) < 2^31)
   __device__ __forceinline__ void set(const AttnParams& p, int g) {
     heads = min(p.hg, p.H - g * p.hg);
-    units = heads * p.QP;
+    first_unit = g * p.hg * p.QP + p.u_base;  // u_base > 0 only with a single group
+    units = heads * p.QP - p.u_base;
     W = units * p.T;
   }
   __device__ __forceinline__ int lo(int c, int G) const { return c * W / G; }
@@ -144,11 +164,13 @@ struct PieceIter {
   // ranges
   int g, ngroups;
   int pos, lo, hi;
+  int wu;  // hybrid: next whole unit of this CTA
   RangeGroup grp;
   __device__ __forceinline__ void init(const AttnParams& p, int cta, int grid) {
     G = grid;
     c = cta;
     pi = cta;
+    wu = cta;
     g = -1;
     ngroups = p.hg > 0 ? (p.H + p.hg - 1) / p.hg : 0;
     pos = hi = lo = 0;
@@ -169,6 +191,16 @@ struct PieceIter {
       pi += G;
       return true;
     }
+    if (wu < p.u_base) {
+      pc.head = wu / p.QP;
+      pc.q_row0 = (wu - pc.head * p.QP) * (2 * kQTile);
+      pc.t0 = 0;
+      pc.n = p.T;
+      pc.whole = true;
+      pc.slot = 0;
+      wu += G;
+      return true;
+    }
     while (pos >= hi) {
       if (++g >= ngroups) return false;
       grp.set(p, g);
@@ -176,9 +208,9 @@ struct PieceIter {
       hi = grp.lo(c + 1, G);
     }
     const int ul = pos / p.T;
-    const int head_l = ul / p.QP;
-    pc.head = g * p.hg + head_l;
-    pc.q_row0 = (ul - head_l * p.QP) * (2 * kQTile);
+    const int u = grp.first_unit + ul;
+    pc.head = u / p.QP;
+    pc.q_row0 = (u - pc.head * p.QP) * (2 * kQTile);
     pc.t0 = pos - ul * p.T;
     const int end = min(hi, (ul + 1) * p.T);
     pc.n = end - pos;
@@ -202,7 +234,7 @@ struct UnitPieces {
     } else {
       g = (u / p.QP) / p.hg;
       grp.set(p, g);
-      start = (u - g * p.hg * p.QP) * p.T;
+      start = (u - grp.first_unit) * p.T;  // callers never pass a whole unit of the hybrid schedule (u < u_base)
       c_first = grp.cta_of(start, p.G);
       np = grp.cta_of(start + p.T - 1, p.G) - c_first + 1;
     }
@@ -280,12 +312,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint64_t* k_empty = bars + 4;            // 2
   uint64_t* v_full = bars + 6;             // 2
   uint64_t* v_empty = bars + 8;            // 2
-  uint64_t* s_full = bars + 10;            // 2 (per query tile)
-  uint64_t* p_full = bars + 12;            // 4: [query tile][half of the KV tile]
-  uint64_t* o_full = bars + 16;            // 1
-  uint64_t* o_empty = bars + 17;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
-  int* merge_ticket = reinterpret_cast<int*>(bars + 20);  // [query tile]: arrival ticket of the current partial piece
+  uint64_t* s_full = bars + 10;            // 4: [query tile][half of the KV tile] (whole-tile variant: [query tile])
+  uint64_t* p_full = bars + 14;            // 4: [query tile][half of the KV tile]
+  uint64_t* o_full = bars + 18;            // 1
+  uint64_t* o_empty = bars + 19;           // 2
+  uint64_t* pv_last = bars + 21;           // 2 (half-tile pipeline): first P.V half of a piece's last KV tile has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  int* merge_ticket = reinterpret_cast<int*>(bars + 24);  // [query tile]: arrival ticket of the current partial piece
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -308,9 +341,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
+        mbar_init(&s_full[2 + i], 1);
         mbar_init(&p_full[2 * i], kSoftmaxWarpsPerTile);
         mbar_init(&p_full[2 * i + 1], kSoftmaxWarpsPerTile);
         mbar_init(&o_empty[i], kSoftmaxWarpsPerTile);
+        mbar_init(&pv_last[i], 1);
       }
       mbar_init(o_full, 1);
       fence_mbar_init();
@@ -398,6 +433,84 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       long long dbg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       const long long tm_begin = clock64();
 #endif
+#if MMPL_ATTN_SPLIT_S
+      // Half-tile pipeline. S_q of a KV tile lives in two independent 64-column halves (KV rows 0-63 / 64-127), each
+      // with its own S-ready and P-ready barrier; bf16 P of a half overwrites the first 32 columns of that half.
+      // Per query tile and half the issue order is  P_h(j).V_h(j)  then  Q.K_h(j+1)^T : the next S half is on its way
+      // as soon as this P half has been consumed, while the softmax warps are still busy with the other half, so
+      // neither the softmax warps nor the tensor pipe wait for a whole-tile round trip (the whole-tile variant measured
+      // 1190 of 2700 clk per tile with the softmax warps waiting for S). The commit on s_full[q][h] that follows
+      // P.V_h(j) and Q.K_h(j+1) also tells the softmax warps that this P.V has completed, which they need to know
+      // before they rescale O; on the last tile of a piece, where no Q.K follows, pv_last[q] does that for half 0.
+      constexpr uint32_t idesc_qk_h = make_idesc_bf16(128, 64, 0, 0);
+      auto issue_qk_half = [&](int qt, int st, int h) {
+        const uint32_t a0 = desc_lo(kDescK) + ((q_addr + qt * 2 * kBoxBytes) >> 4);
+        const uint32_t b0 = desc_lo(kDescK) + ((k_addr + st * 2 * kBoxBytes + h * 64 * 128) >> 4);  // KV rows h*64 ..
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * (kBoxBytes >> 4) + 2 * (k & 3);
+          umma_ss_elect(tmem_base + qt * 128 + h * 64, a0 + off, desc_hi(kDescK), b0 + off, desc_hi(kDescK), idesc_qk_h,
+                        k != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv_half = [&](int qt, int st, int h, bool first) {
+        const uint32_t b0 = desc_lo(kDescV) + ((v_addr + st * 2 * kBoxBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = h * 4 + kk;
+          umma_ts_elect(tmem_base + 256 + qt * 128, tmem_base + qt * 128 + h * 64 + 8 * kk, b0 + k * (2048 >> 4),
+                        desc_hi(kDescV), idesc_pv, (first && kk == 0) ? 0u : 1u);
+        }
+      };
+      int g = 0, piece = 0;
+      PieceIter pit;
+      pit.init(p, blockIdx.x, G);
+      Piece pc;
+      for (; pit.next(p, pc); ++piece) {
+        const int n = pc.n;
+        mbar_wait(q_full, piece & 1);
+        mbar_wait(&k_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        for (int qt = 0; qt < 2; ++qt)
+          for (int h = 0; h < 2; ++h) {
+            issue_qk_half(qt, g & 1, h);
+            tc_commit_elect(&s_full[2 * qt + h]);
+          }
+        tc_commit_elect(&k_empty[g & 1]);
+        if (n == 1) tc_commit_elect(q_empty);
+        for (int jj = 0; jj < n; ++jj) {
+          const int gj = g + jj;
+          const int st = gj & 1;
+          const uint32_t ph = (gj >> 1) & 1;
+          const int stn = (gj + 1) & 1;
+          const uint32_t phn = ((gj + 1) >> 1) & 1;
+          const bool more = jj + 1 < n;
+          mbar_wait(&v_full[st], ph);
+          for (int qt = 0; qt < 2; ++qt) {
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(&p_full[2 * qt + h], gj & 1);
+              if (jj == 0 && h == 0) mbar_wait(&o_empty[qt], (piece & 1) ^ 1);  // previous piece's O has been read out
+              if (qt == 0 && h == 0 && more) mbar_wait(&k_full[stn], phn);
+              tc_fence_after();
+              issue_pv_half(qt, st, h, jj == 0 && h == 0);
+              if (more) {
+                issue_qk_half(qt, stn, h);
+                tc_commit_elect(&s_full[2 * qt + h]);
+              } else if (h == 0) {
+                tc_commit_elect(&pv_last[qt]);
+              }
+            }
+          }
+          tc_commit_elect(&v_empty[st]);
+          if (more) {
+            tc_commit_elect(&k_empty[stn]);
+            if (jj + 2 == n) tc_commit_elect(q_empty);  // last QK of the piece issued: Q smem may be reloaded
+          }
+        }
+        tc_commit_elect(o_full);
+        g += n;
+      }
+#else
       int g = 0, piece = 0;
       PieceIter pit;
       pit.init(p, blockIdx.x, G);
@@ -461,6 +574,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tc_commit_elect(o_full);
         g += n;
       }
+#endif  // MMPL_ATTN_SPLIT_S
 #if MMPL_ATTN_TIMING
       dbg[12] = clock64() - tm_begin;
       if (blockIdx.x == 0 && lane == 0)
@@ -480,12 +594,102 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     long long dbg[4] = {0, 0, 0, 0};
 #endif
     int g = 0, piece = 0;
+    int sbase = 0;  // half-tile pipeline: phases of s_full[qt][*] consumed by earlier pieces
     PieceIter pit;
     pit.init(p, blockIdx.x, G);
     Piece pc;
     for (; pit.next(p, pc); ++piece) {
       const int t0 = pc.t0, n = pc.n, head = pc.head;
       const int q_row = pc.q_row0 + row_in_unit;
+#if MMPL_ATTN_SPLIT_S
+      float m_run = -INFINITY;  // running max, in the scaled log2 domain
+      float l_run = 0.f;
+      TileIter it;
+      it.init(p, t0);
+      for (int jj = 0; jj < n; ++jj, it.next(p)) {
+        const int valid = it.valid();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int valid_h = valid - h * 64;  // valid KV rows in this half (<= 0: none; >= 64: all)
+          TSTAMP(ts0);
+          mbar_wait(&s_full[2 * qt + h], (sbase + jj) & 1);
+          tc_fence_after();
+          TSTAMP(ts1);
+          uint32_t sv[64];
+          tmem_ld_32x32(t_s + h * 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+          tmem_ld_32x32(t_s + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+          tmem_ld_wait();
+          if (valid_h < 64) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (c >= valid_h) sv[c] = 0xFF800000u;  // -inf
+          }
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains of 3-input max
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            mx4[c & 3] = fmaxf(fmaxf(mx4[c & 3], __uint_as_float(sv[2 * c])), __uint_as_float(sv[2 * c + 1]));
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          const float m_new = fmaxf(m_run, mx * p.scale_log2);
+          const bool grow = m_new > m_run + 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float alpha = fast_exp2(m_run - m_new);
+            l_run *= alpha;
+            m_run = m_new;
+            if (jj > 0 || h > 0) {
+              // O holds the P.V of every half before this one; the last of them may still be executing (or not even
+              // issued). The commit that follows it is the next phase of the *other* half's S barrier: after P.V_b(jj-1)
+              // comes S_b(jj) (h == 0), after P.V_a(jj) comes S_a(jj+1) (h == 1) or, on the last tile, pv_last. No
+              // later P.V can start before this warp group has delivered the P of this half.
+              if (h == 1 && jj + 1 == n) mbar_wait(&pv_last[qt], piece & 1);
+              else mbar_wait(&s_full[2 * qt + (h ^ 1)], (sbase + jj + h) & 1);
+              tc_fence_after();
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(t_o + c * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32(t_o + c * 32, o);
+              }
+            }
+          }
+          uint64_t sum2 = pack_f32x2(0.f, 0.f);
+          const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+          const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sc2, nm2);
+            float p0, p1;
+            if (pair_is_poly(c)) {
+              exp2_poly_x2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f32x2(x2, x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
+            pk[c] = pack_bf16x2(p0, p1);
+          }
+          {
+            float s_lo, s_hi;
+            unpack_f32x2(sum2, s_lo, s_hi);
+            l_run += s_lo + s_hi;
+          }
+          TSTAMP(ts2);
+          tmem_st_32x32(t_s + h * 64, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[2 * qt + h]);
+          TSTAMP(ts3);
+          TACC(0, ts1 - ts0); TACC(1, ts2 - ts1); TACC(2, ts3 - ts2); TACC(3, 1);
+        }
+      }
+      sbase += n;
+#else
       float m_run = -INFINITY;  // running max, in the scaled log2 domain
       float l_run = 0.f;
       TileIter it;
@@ -573,6 +777,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         TSTAMP(ts3);
         TACC(0, ts1 - ts0); TACC(1, ts2 - ts1); TACC(2, ts3 - ts2); TACC(3, 1);
       }
+#endif  // MMPL_ATTN_SPLIT_S
       // piece epilogue
       mbar_wait(o_full, piece & 1);
       tc_fence_after();
@@ -645,37 +850,49 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (merge_ticket[qt] == up.count(p) - 1) {
           __threadfence();
           if ((warp & 3) == 0 && lane == 0) p.merge_cnt[2 * u + qt] = 0;  // re-armed for the next launch
+          // Lane = row for the (max, sum) statistics; the O rows are then read one row per warp instruction (512 B,
+          // coalesced; lane = 4 columns), 32 rows in flight per piece, with the row's weight broadcast by shuffle.
           float M = -INFINITY;
           for (int i = 0; i < up.np; ++i) {
             const int sl = up.slot(p, i);
             if (sl >= 0) M = fmaxf(M, __ldcg(p.part_ml + (static_cast<int64_t>(sl) * kUnitRows + row_in_unit) * 2));
           }
           float L = 0.f;
-          float acc[kHD];
-#pragma unroll
-          for (int c = 0; c < kHD; ++c) acc[c] = 0.f;
           for (int i = 0; i < up.np; ++i) {
             const int sl = up.slot(p, i);
             if (sl < 0) continue;
-            const int64_t r = static_cast<int64_t>(sl) * kUnitRows + row_in_unit;
-            const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + r * 2));
-            const float w = exp2f(ml.x - M);
-            L += w * ml.y;
-            const float4* src = reinterpret_cast<const float4*>(p.part_o + r * kHD);
-#pragma unroll
-            for (int c = 0; c < kHD / 4; ++c) {
-              const float4 v = __ldcg(src + c);
-              acc[4 * c] += w * v.x; acc[4 * c + 1] += w * v.y; acc[4 * c + 2] += w * v.z; acc[4 * c + 3] += w * v.w;
-            }
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (static_cast<int64_t>(sl) * kUnitRows + row_in_unit) * 2));
+            L += exp2f(ml.x - M) * ml.y;
           }
-          if (q_row < p.Lq) {
-            const float inv = 1.0f / L;
-            __nv_bfloat16* orow = p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD;
+          const float inv = 1.0f / L;
+          const int warp_row0 = qt * kQTile + lane_base;  // first row (within the unit) of this warp
+          const int rows_ok = p.Lq - (pc.q_row0 + warp_row0);
+#pragma unroll 1
+          for (int hr = 0; hr < 32; hr += 16) {  // 16 rows at a time: 64 accumulator + 64 load registers
+            float4 acc[16];
 #pragma unroll
-            for (int c = 0; c < kHD / 8; ++c)
-              *reinterpret_cast<uint4*>(orow + c * 8) =
-                  make_uint4(pack_bf16x2(acc[8 * c] * inv, acc[8 * c + 1] * inv), pack_bf16x2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv),
-                             pack_bf16x2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv), pack_bf16x2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv));
+            for (int r = 0; r < 16; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < up.np; ++i) {
+              const int sl = up.slot(p, i);
+              if (sl < 0) continue;
+              const int64_t r0 = static_cast<int64_t>(sl) * kUnitRows + warp_row0;
+              const float w_own = exp2f(__ldcg(p.part_ml + (r0 + lane) * 2) - M) * inv;
+              const float4* src = reinterpret_cast<const float4*>(p.part_o + (r0 + hr) * kHD) + lane;
+              float4 v[16];
+#pragma unroll
+              for (int r = 0; r < 16; ++r) v[r] = __ldcg(src + r * (kHD / 4));
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                const float w = __shfl_sync(0xffffffffu, w_own, hr + r);
+                acc[r].x += w * v[r].x; acc[r].y += w * v[r].y; acc[r].z += w * v[r].z; acc[r].w += w * v[r].w;
+              }
+            }
+            __nv_bfloat16* obase = p.out + static_cast<int64_t>(pc.q_row0 + warp_row0 + hr) * p.ldo + head * kHD + lane * 4;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              if (hr + r < rows_ok)
+                *reinterpret_cast<uint2*>(obase + static_cast<int64_t>(r) * p.ldo) =
+                    make_uint2(pack_bf16x2(acc[r].x, acc[r].y), pack_bf16x2(acc[r].z, acc[r].w));
           }
         }
       }
@@ -708,6 +925,7 @@ attn_combine_kernel(const AttnParams p) {
   const int lane = threadIdx.x & 31;
   const int head = u / p.QP;
   const int q_row = (u - head * p.QP) * kUnitRows + row_in_unit;
+  if (u < p.u_base) return;          // hybrid schedule: ran whole
   UnitPieces up;
   up.init(p, u);
   const int np = up.np;
@@ -758,7 +976,7 @@ static size_t g_merge_cnt_n = 0;
 int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,
                     int64_t ldkv0, int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1,
                     int nseg, const int* seg_start, const int* seg_rows, const int* seg_src, void* out,
-                    int64_t ldo, float softmax_scale, int force_split, cudaStream_t stream) {
+                    int64_t ldo, float softmax_scale, int force_split, int force_ctas, cudaStream_t stream) {
   MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "flash_attn: requires an sm_100 device");
   MMPL_CHECK(Lq > 0 && H > 0, MMPL_ERR_SHAPE, "flash_attn: bad Lq=%d H=%d", Lq, H);
   MMPL_CHECK(nseg >= 1 && nseg <= kMaxSeg, MMPL_ERR_SHAPE, "flash_attn: nseg=%d out of [1,%d]", nseg, kMaxSeg);
@@ -798,7 +1016,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   p.QP = (Lq + kUnitRows - 1) / kUnitRows;
   p.T = T;
   const int U = p.QP * H;
-  const int sms = sm_count();
+  const int sms = (force_ctas > 0 && force_ctas < sm_count()) ? force_ctas : sm_count();  // CTAs of the persistent grid
   const double piece_fixed = 6.0, merge_per_piece = 0.0291, merge_fixed = 6.0;  // merge_fixed: the combine launch itself
   int best_split = 1;
   double best = 1e30;
@@ -813,29 +1031,63 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   // stays L2-resident: measured on B200 (profiles/README.md) 6 % faster than the best uniform split for L_kv = 9360
   // and 14040 at cfg2 (58 / 86 MB of K/V), slower from 115 MB up, erratic with several head groups. Hence: one group
   // of all heads, only below the L2 budget, and only when the cost model prefers it.
-  int hg = 0;
+  int hg = 0, u_base = 0;
   {
     static const int l2_mb = getenv("MMPL_ATTN_L2_MB") ? atoi(getenv("MMPL_ATTN_L2_MB")) : 90;
     static const int mode_env = getenv("MMPL_ATTN_RANGES") ? atoi(getenv("MMPL_ATTN_RANGES")) : -1;  // 0 never, 1 whenever possible, -1 cost model
-    const double kv_mb = static_cast<double>(H) * T * kKVTile * 512.0 / (1 << 20);
+    static const int hybrid_env = getenv("MMPL_ATTN_HYBRID") ? atoi(getenv("MMPL_ATTN_HYBRID")) : -1;  // same
+    const double head_mb = static_cast<double>(T) * kKVTile * 512.0 / (1 << 20);
+    const double kv_mb = H * head_mb;
     const double pieces_per_cta = static_cast<double>(U) / sms + 1.0;
     const double cost_ranges = static_cast<double>(U) * T / sms + piece_fixed * pieces_per_cta + merge_fixed + merge_per_piece * 2.0 * sms;
     const bool fits32 = static_cast<long long>(U) * T * (sms + 1) < (1ll << 31);  // PieceIter's range arithmetic is 32-bit
     const bool possible = T >= 16 && static_cast<long long>(U) * T >= 8ll * sms && kv_mb <= l2_mb && fits32;
-    if (possible && (mode_env == 1 || (mode_env < 0 && cost_ranges < best))) hg = H;
+    if (possible && (mode_env == 1 || (mode_env < 0 && cost_ranges < best))) { hg = H; best = cost_ranges; }
+    // Hybrid schedule: floor(U/G) rounds of whole units in lockstep, the remaining U mod G units as ranges (merged in
+    // the kernel). Same tile count per CTA as the pure range schedule, but only the heads of the ranged units are read
+    // by free-running CTAs, so it stays inside L2 where the pure range schedule does not (cfg2 at L_kv = 32760: 5 of
+    // 12 heads, 84 MB), and it has no merge kernel, which the uniform split pays for (37 us per launch there).
+    const int rounds = U / sms, rem = U - rounds * sms;
+    if (rounds >= 1 && rem > 0) {
+      const int heads2 = H - (rounds * sms) / p.QP;  // heads the ranged units belong to
+      const double cost_hybrid = static_cast<double>(U) * T / sms + piece_fixed * (rounds + 2.0);
+      const bool hybrid_possible = T >= 16 && static_cast<long long>(rem) * T >= 6ll * sms && heads2 * head_mb <= l2_mb && fits32;
+      // (while the K/V of all heads is small against L2 the pure range schedule is as good or better — measured 129 vs
+      //  136 us at L_kv = 4680, level at 9360: its merges are spread over the kernel instead of all at the tail)
+      static const int ranges_mb = getenv("MMPL_ATTN_RANGES_MB") ? atoi(getenv("MMPL_ATTN_RANGES_MB")) : 45;
+      const bool ranges_better = hg > 0 && kv_mb <= ranges_mb;
+      if (hybrid_possible && (hybrid_env == 1 || (hybrid_env < 0 && cost_hybrid < best && !ranges_better))) {
+        hg = H;
+        u_base = rounds * sms;
+        best = cost_hybrid;
+      }
+    }
   }
   if (force_split > 0 && force_split <= T) {
     best_split = force_split;
     hg = 0;
+    u_base = 0;
+  } else if (force_split <= -1000) {
+    // test hook: hybrid schedule whenever there is at least one whole round and something left over
+    const int rounds = U / sms, rem = U - rounds * sms;
+    hg = 0;
+    u_base = 0;
+    if (rounds >= 1 && rem > 0 && static_cast<long long>(rem) * T >= 2ll * sms &&
+        static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
+      hg = H;
+      u_base = rounds * sms;
+    }
   } else if (force_split < 0 && T >= 2 && static_cast<long long>(U) * T >= 2ll * sms &&
              static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
     hg = -force_split < H ? -force_split : H;  // test hook: range schedule with this many heads per group
+    u_base = 0;
   }
   static const bool nonpersistent = getenv("MMPL_ATTN_NONPERSISTENT") != nullptr;
   int G;
   size_t slots = 0;
   if (hg > 0) {
     p.hg = hg;
+    p.u_base = u_base;
     p.split = 1;
     p.n_pieces = 0;
     G = sms;

@@ -17,6 +17,7 @@ int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
                     int64_t ldo, float softmax_scale, cudaStream_t stream);
 
 void flash_attn_force_split(int split);
+void flash_attn_force_ctas(int ctas);
 
 int ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                 const void* scale, int64_t mod_stride, int rows_per_frame, cudaStream_t st);

@@ -190,6 +190,56 @@ def test_flash_attn_range_schedule(Lq, Lk, H, hg):
     _report("ranges over segments", got_seg, O.attention(q, k[idx], v[idx]), atol=1e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("Lq,Lk,H,ctas", [(700, 5000, 3, 4), (700, 5000, 3, 7), (1300, 2100, 5, 6), (4680, 4680, 12, 0),
+                                          (4680, 18720, 12, 0), (3120, 6000, 40, 0), (600, 40000, 2, 5)])
+def test_flash_attn_hybrid_schedule(Lq, Lk, H, ctas):
+    """The hybrid schedule (attention_tcgen05.cu: u_base > 0): floor(U/G) rounds of whole units, the other U mod G
+    units cut into equal ranges and merged inside the kernel. Forced with split <= -1000; `ctas` shrinks the persistent
+    grid so that small problems have more units than CTAs (0 = one CTA per SM: the cfg2 / 14B-width shapes, where the
+    cost model picks this schedule by itself). Checked against the oracle, the whole-unit schedule, for determinism
+    and over row segments."""
+    from mmpl_b200 import _lib
+    ops, lib = _ops(), _lib.load()
+    q, k, v = _rand(Lq, H, 128, seed=1), _rand(Lk, H, 128, seed=2), _rand(Lk, H, 128, seed=3)
+    segs = [(0, Lk // 3 + 17), (Lk // 2, Lk // 2 - 5)]
+    idx = torch.cat([torch.arange(a, a + n) for a, n in segs]).to(DEV)
+    try:
+        lib.mmpl_attn_set_ctas(ctas)
+        lib.mmpl_attn_set_split(1)
+        whole = ops.flash_attn(q, k, v)
+        lib.mmpl_attn_set_split(-1000)
+        got = ops.flash_attn(q, k, v)
+        got2 = ops.flash_attn(q, k, v)
+        got_seg = ops.flash_attn(q, k, v, segments=segs)
+        lib.mmpl_attn_set_split(0)
+        auto = ops.flash_attn(q, k, v)
+    finally:
+        lib.mmpl_attn_set_split(0)
+        lib.mmpl_attn_set_ctas(0)
+    ref = O.attention(q, k, v)
+    _report(f"attn hybrid {Lq}x{Lk}x{H} ctas={ctas}", got, ref, atol=1e-2, rtol=2e-2)
+    _report("hybrid vs whole units", got, whole, atol=1e-2, rtol=2e-2)
+    _report("cost-model schedule", auto, ref, atol=1e-2, rtol=2e-2)
+    assert torch.equal(got, got2), "hybrid schedule is not deterministic"
+    _report("hybrid over segments", got_seg, O.attention(q, k[idx], v[idx]), atol=1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("half", [0, 1])
+def test_flash_attn_both_pipelines_variant(half):
+    """The library holds two builds of flash_attn_kernel (attention_tcgen05.cu: MMPL_ATTN_SPLIT_S): the whole-tile S
+    hand-over and the half-tile S pipeline; the dispatcher picks by KV length (half-tile for <= 8 KV tiles per unit).
+    MMPL_ATTN_HALF=0|1 forces one for every call (read once per process, hence the subprocess): every attention test of
+    this file - all shapes, forced splits, range and hybrid schedules, segments, lazy rescale - must pass with either."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, MMPL_ATTN_HALF=str(half))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "flash_attn and not variant and not merge_kernel_fallback"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_flash_attn_merge_kernel_fallback():
     """Partial pieces are merged inside flash_attn_kernel (default for the range schedule) or by attn_combine_kernel
     (default for the uniform split); MMPL_ATTN_MERGE=inline|kernel forces one for both schedules (read once per process,
