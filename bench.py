@@ -322,9 +322,11 @@ def run_ours(args):
                      "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(achieved_tf / peak_tf, 4),
                      # dram__bytes_read.sum + dram__bytes_write.sum of the L_kv = 32760 launch in
-                     # profiles/r01_ncu_attention_vs_cudnn.txt (ncu --set full): 231.9 MB + 63.1 MB; its algorithmic K/V + Q + O
-                     # bytes are 230 MB, the rest is the split-KV workspace
-                     "traffic": 294.9e6, "traffic_launch": "L_kv=32760, S=4680, 12 heads",
+                     # profiles/r01_ncu_attention_hybrid_vs_cudnn.txt (ncu --set full): 350.5 MB + 24.5 MB; its algorithmic
+                     # K/V + Q + O bytes are 230 MB, the rest is K/V read a second time by the ranged units of the hybrid
+                     # schedule (5 of 12 heads) and their partials (the uniform split it replaced: 231.9 + 63.1 MB and a
+                     # merge kernel with 88 MB more)
+                     "traffic": 375.0e6, "traffic_launch": "L_kv=32760, S=4680, 12 heads",
                      "flops_per_launch_avg": round(attn_flops / max(attn_n, 1)), "peak_source": peak_src,
                      "launches": int(attn_n), "ms_in_timed_region": round(attn_ms, 2),
                      "share_of_step": round(attn_ms / ms_total, 4)},
