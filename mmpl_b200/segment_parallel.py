@@ -12,6 +12,10 @@ ranks -- lane 0 the conditional branch, lane 1 the unconditional one -- which ho
 hands its copy of the anchors to the same lane of the next segment's pair. One prompt's chain saturates at
 T_segment / T_anchor ~ 3 segment slots; the pair split halves both times, which is what lets one
 chain use 8 GPUs (4 slots x 2 lanes).
+
+Box throughput beyond one chain's saturation point comes from independent chains (different prompts / seeds) on
+disjoint rank groups (`make_chain_groups`): an AnchorChannel built on a chain's group addresses ranks relative to that
+group, so a chain's schedule does not depend on where in the box it runs, and chains never exchange data.
 """
 from __future__ import annotations
 
@@ -35,6 +39,26 @@ def producer_of(segment: int, world: int, lanes: int = 1, lane: int = 0) -> int:
     return (segment % (world // lanes)) * lanes + lane
 
 
+def make_chain_groups(chains: int, world: Optional[int] = None, rank: Optional[int] = None):
+    """Splits the world into `chains` contiguous rank groups of equal size (one independent video each). Every rank
+    must call this (torch.distributed.new_group is collective); returns (chain index of this rank, its group, ranks of
+    the group). With chains == 1 the group is None (= the default group)."""
+    world = dist.get_world_size() if world is None else world
+    rank = dist.get_rank() if rank is None else rank
+    if chains < 1 or world % chains:
+        raise ValueError(f"world size {world} is not a multiple of chains={chains}")
+    per = world // chains
+    mine = rank // per
+    if chains == 1:
+        return 0, None, list(range(world))
+    group = None
+    for c in range(chains):  # same order on every rank
+        g = dist.new_group(list(range(c * per, (c + 1) * per)))
+        if c == mine:
+            group = g
+    return mine, group, list(range(mine * per, (mine + 1) * per))
+
+
 def default_segment_connect(anchors: torch.Tensor) -> torch.Tensor:
     """Stand-in for the reference's "segment connect" (decode anchors with the VAE, take pixel frames 8:13, re-encode,
     keep the first 2 latents; Wan_fps_inference_parallel_4gpu_20s.py:191-205): the VAE is outside the hot path and its
@@ -53,6 +77,8 @@ class AnchorChannel:
             raise ValueError(f"world size {self.world} is not a multiple of lanes={lanes}")
         self.lanes = lanes
         self.lane = self.rank % lanes
+        # ranks below are relative to `group`; point-to-point calls take global ranks
+        self._global = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
         self._local: Dict[int, torch.Tensor] = {}
         self._pending = []
         self.bytes_sent = 0
@@ -64,14 +90,14 @@ class AnchorChannel:
         if dst == self.rank:
             self._local[segment + 1] = payload.clone()
             return
-        self._pending.append((dist.isend(payload, dst=dst, group=self.group, tag=segment + 1), payload))
+        self._pending.append((dist.isend(payload, dst=self._global(dst), group=self.group, tag=segment + 1), payload))
 
     def recv(self, segment: int, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Tensor:
         src = producer_of(segment - 1, self.world, self.lanes, self.lane)
         if src == self.rank:
             return self._local.pop(segment)
         buf = torch.empty(tuple(shape), dtype=dtype, device=device)
-        dist.recv(buf, src=src, group=self.group, tag=segment)
+        dist.recv(buf, src=self._global(src), group=self.group, tag=segment)
         return buf
 
     def flush(self) -> None:

@@ -7,8 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mmpl_b200.segment_parallel import (AnchorChannel, SegmentParallelRunner, default_segment_connect, producer_of,
-                                        segments_of_rank)
+from mmpl_b200.segment_parallel import (AnchorChannel, SegmentParallelRunner, default_segment_connect, make_chain_groups,
+                                        producer_of, segments_of_rank)
 
 
 def test_round_robin_placement():
@@ -84,6 +84,49 @@ def test_anchor_handoff_world2_gloo(num_segments):
     assert ("send", 0, 1) in logs[0] and ("recv", 1, 0) in logs[1]
 
 
+def _chain_worker(rank, world, port, chains, num_segments, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chain, group, ranks = make_chain_groups(chains)
+        runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(group=group), anchor_shape=(1, 8, 4, 2, 2))
+        outs = runner.run(lambda seg: torch.full((1, 21, 4, 2, 2), float(chain * 1000 + seg * 100)), ["p"], num_segments)
+        q.put((rank, chain, ranks, {k: v[0, :, 0, 0, 0].tolist() for k, v in outs.items()}, runner.log))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_independent_chains_world4_gloo():
+    """Two independent chains on disjoint rank groups of a 4-rank world (2 segment slots each): every chain follows the
+    same group-relative schedule, its anchors stay inside its group, and its result equals the sequential chain."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    num_segments = 3
+    procs = [ctx.Process(target=_chain_worker, args=(r, 4, port, 2, num_segments, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    outs = {0: {}, 1: {}}
+    for rank, chain, ranks, o, log in res:
+        assert chain == rank // 2 and ranks == [2 * chain, 2 * chain + 1]
+        assert sorted(o) == segments_of_rank(rank % 2, 2, num_segments)
+        assert all(peer in (0, 1) for _, _, peer in log)  # group-relative peers only
+        outs[chain].update(o)
+    for chain in (0, 1):
+        prev = None
+        for seg in range(num_segments):
+            base = [float(chain * 1000 + seg * 100)] * 21
+            if prev is not None:
+                base[0], base[1] = prev[19], prev[20]
+            expect = [b + 1.0 for b in base]
+            assert outs[chain][seg] == expect, (chain, seg)
+            prev = expect
+
+
 def test_single_rank_runs_all_segments_locally():
     runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(), anchor_shape=(1, 8, 4, 2, 2))
     outs = runner.run(lambda seg: torch.zeros(1, 21, 4, 2, 2), ["p"], 3)
@@ -150,8 +193,10 @@ def _cfg_worker(rank, world, port, q):
     try:
         pipe, tags = _fps_pipeline(cfg_group=dist.group.WORLD)
         latents, sent = _fps_run(pipe)
-        q.put((rank, latents, sent[0], sorted(set(tags)), len(tags), pipe.kv_cache_pos is None, pipe.kv_cache_neg is None,
-               pipe.cfg_bytes_exchanged))
+        # numpy arrays travel through the queue by value; torch tensors would go through shared-memory handles that die
+        # with this process (a race with the parent's q.get)
+        q.put((rank, latents.float().numpy(), sent[0].float().numpy(), sorted(set(tags)), len(tags), pipe.kv_cache_pos is None,
+               pipe.kv_cache_neg is None, pipe.cfg_bytes_exchanged))
     finally:
         dist.destroy_process_group()
 
@@ -173,8 +218,8 @@ def test_cfg_pair_split_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, latents, anchors, seen, n, pos_none, neg_none, nbytes in res:
-        assert torch.equal(latents, ref_latents), f"rank {rank}: latents differ from the single-process run"
-        assert torch.equal(anchors, ref_sent[0])
+        assert torch.equal(torch.from_numpy(latents), ref_latents.float()), f"rank {rank}: latents differ from the single-process run"
+        assert torch.equal(torch.from_numpy(anchors), ref_sent[0].float())
         assert seen == (["pos"] if rank == 0 else ["neg"]) and n == n_forwards // 2
         assert (pos_none, neg_none) == ((False, True) if rank == 0 else (True, False))
         # 4 stages x 3 steps, flow of n frames [1, n, 16, 8, 12] fp32 in this CPU test

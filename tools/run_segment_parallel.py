@@ -8,6 +8,8 @@ One process per GPU; segment k runs on rank k % G; anchors go rank -> rank over 
 Prints one JSON line with denoised latent frames/s per box = segments * 21 / wall time of the whole chain (device
 time, max over ranks), the per-segment times and the anchor bytes moved. `--sampling-steps` below the reference's 50
 shortens every stage proportionally (same schedule, same kernels, fewer UniPC steps) for quick scaling checks.
+`--chains C` runs C independent videos on disjoint groups of world/C ranks (box throughput beyond the point where one
+chain saturates); `--cfg-pair` splits every segment over two ranks (conditional / unconditional branch).
 """
 import argparse
 import json
@@ -27,7 +29,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mmpl_b200.causal_model import CausalFPSWanModel  # noqa: E402
 from mmpl_b200.pipeline import CausalFPSInferencePipeline  # noqa: E402
 from mmpl_b200.segment_parallel import (AnchorChannel, I2V_ANCHOR_SHAPE, SegmentParallelRunner,  # noqa: E402
-                                        T2V_ANCHOR_SHAPE)
+                                        T2V_ANCHOR_SHAPE, make_chain_groups)
 from mmpl_b200.wan_wrapper import MODEL_CONFIGS, WanFPSWrapper  # noqa: E402
 
 
@@ -38,6 +40,8 @@ def main():
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
     ap.add_argument("--i2v", action="store_true")
+    ap.add_argument("--chains", type=int, default=1,
+                    help="independent videos (own prompt / noise) on disjoint rank groups of world/chains ranks each: box throughput")
     ap.add_argument("--cfg-pair", action="store_true",
                     help="CFG-pair split: two ranks per segment (conditional / unconditional branch), world must be even")
     a = ap.parse_args()
@@ -58,7 +62,13 @@ def main():
     model = model.to(torch.bfloat16).eval().requires_grad_(False)
     gen = WanFPSWrapper(model=model, timestep_shift=5.0)
     build_s = time.perf_counter() - t0
-    prompt = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).to(dev)
+    chain, chain_group, chain_ranks = (0, None, list(range(world)))
+    if world > 1:
+        chain, chain_group, chain_ranks = make_chain_groups(a.chains)
+    elif a.chains != 1:
+        raise SystemExit("--chains needs torchrun with a multiple of that many ranks")
+    cworld, crank = len(chain_ranks), rank - chain_ranks[0]
+    prompt = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(1 + 10 * chain)).to(torch.bfloat16).to(dev)
     negative = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(dev)
 
     class Text(torch.nn.Module):
@@ -74,7 +84,7 @@ def main():
     lanes = 2 if a.cfg_pair else 1
     cfg_group = None
     if a.cfg_pair:
-        assert world % 2 == 0, "--cfg-pair needs an even number of ranks"
+        assert cworld % 2 == 0, "--cfg-pair needs an even number of ranks per chain"
         for s in range(world // 2):  # every rank creates every pair group, in the same order
             grp = dist.new_group([2 * s, 2 * s + 1])
             if rank // 2 == s:
@@ -82,20 +92,20 @@ def main():
     torch.manual_seed(1234)  # the pipeline draws its re-noising noise with torch.randn_like: same stream on both lanes
     pipe = CausalFPSInferencePipeline(args, dev, generator=gen, text_encoder=Text(), vae=VAE(), device_cond=dev, device_uncond=dev,
                                       cfg_group=cfg_group)
-    channel = AnchorChannel(lanes=lanes)
+    channel = AnchorChannel(group=chain_group, lanes=lanes)
     if cfg_group is not None:  # create the pair's communicator outside the timed region
         warm = [torch.zeros(8, device=dev), torch.zeros(8, device=dev)]
         dist.all_gather(warm, torch.zeros(8, device=dev), group=cfg_group)
-    if world > lanes:  # create the NCCL point-to-point connections outside the timed region
+    if cworld > lanes:  # create the NCCL point-to-point connections outside the timed region
         buf = torch.zeros(8, device=dev)
-        nxt, prv = (rank + lanes) % world, (rank - lanes) % world
-        ops = [dist.P2POp(dist.isend, buf, nxt), dist.P2POp(dist.irecv, torch.empty_like(buf), prv)]
+        nxt, prv = chain_ranks[(crank + lanes) % cworld], chain_ranks[(crank - lanes) % cworld]
+        ops = [dist.P2POp(dist.isend, buf, nxt, chain_group), dist.P2POp(dist.irecv, torch.empty_like(buf), prv, chain_group)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     runner = SegmentParallelRunner(pipe, channel, anchor_shape=I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE)
 
     def make_noise(seg):
-        g = torch.Generator().manual_seed(100 + seg)
+        g = torch.Generator().manual_seed(100 + seg + 1000 * chain)
         return torch.randn(1, 21, 16, 60, 104, generator=g).to(torch.bfloat16).to(dev)
 
     if a.i2v:  # the i2v schedule needs a first frame for segment 0 (VAE-encoded image in the reference)
@@ -127,7 +137,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     finite = all(torch.isfinite(v.float()).all().item() for v in outs.values())
-    info = dict(rank=rank, segments=sorted(outs), ms=my_ms, launches=model.launch_count(), finite=finite,
+    info = dict(rank=rank, chain=chain, segments=sorted(outs), ms=my_ms, launches=model.launch_count(), finite=finite,
                 anchor_bytes_sent=channel.bytes_sent, cfg_bytes_exchanged=getattr(pipe, "cfg_bytes_exchanged", 0), log=runner.log,
                 checksum={k: float(v.float().abs().sum()) for k, v in outs.items()})
     gathered = [info]
@@ -137,10 +147,10 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
-            "value": a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
-            "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.segments} segments x 21 latent frames 60x104, "
+            "value": a.chains * a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
+            "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.chains} chain(s) x {a.segments} segments x 21 latent frames 60x104, "
                                    f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
-                       "parallelism": (f"segment-parallel x{world // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
+                       "parallelism": ((f"{a.chains} independent chains, each " if a.chains > 1 else "") + f"segment-parallel x{cworld // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
                                        ", anchors over NCCL send/recv")},
             "model_build_s": build_s, "ranks": gathered}))
     if world > 1:
