@@ -73,6 +73,14 @@ int mmpl_attn_set_split(int split);
 /* Test hook: run the persistent attention grid with `ctas` CTAs instead of one per SM (0 = default), so that small
  * problems exercise the multi-round schedules. */
 int mmpl_attn_set_ctas(int ctas);
+/* Host-only (no GPU needed): the work partition mmpl_flash_attn would use for Lq query rows, H heads and kv_tiles
+ * 128-row KV tiles per unit on a persistent grid of `ctas` CTAs (force_split as in mmpl_attn_set_split).
+ * sched[7] = {schedule (0 uniform split, 1 ranges, 2 hybrid), split, heads per group, whole units, grid size, workspace
+ * slots, query-tile pairs per head}; pieces[max_pieces][9] = {cta, head, q_row0, first KV tile, KV tiles, whole, slot,
+ * pieces of the unit according to the merge bookkeeping, slot found by it}. Returns the number of pieces,
+ * MMPL_ERR_SHAPE if max_pieces is too small, MMPL_ERR_ARG for invalid arguments. Used by the CPU tests to check that every (query tile pair,
+ * KV tile) is covered exactly once by every schedule. */
+int mmpl_attn_plan(int Lq, int H, int kv_tiles, int ctas, int force_split, int* sched, int* pieces, int max_pieces);
 /* Tuning / test hook: stream-K tail schedule of the cta_group::2 GEMM: 0 = never (default; slower on B200 at the
  * cfg2 shapes, see gemm_tcgen05.cu), -1 = automatic (when whole 256x256 tiles would leave more than 4 % of the last
  * wave empty), 1 = whenever tiles % pairs != 0. */

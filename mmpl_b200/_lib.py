@@ -51,6 +51,7 @@ SIGNATURES = {
     "mmpl_gemm_set_streamk": (c_int, [c_int]),
     "mmpl_attn_set_split": (c_int, [c_int]),
     "mmpl_attn_set_ctas": (c_int, [c_int]),
+    "mmpl_attn_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int]),
     "mmpl_ln_modulate": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_int64, c_int, c_void_p]),
     "mmpl_ln_affine": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),

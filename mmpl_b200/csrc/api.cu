@@ -145,6 +145,11 @@ int mmpl_attn_set_ctas(int ctas) {
   return MMPL_OK;
 }
 
+int mmpl_attn_plan(int Lq, int H, int kv_tiles, int ctas, int force_split, int* sched, int* pieces, int max_pieces) {
+  if (Lq <= 0 || H <= 0 || kv_tiles <= 0 || ctas <= 0 || !pieces || max_pieces <= 0) return MMPL_ERR_ARG;
+  return flash_attn_plan(Lq, H, kv_tiles, ctas, force_split, sched, pieces, max_pieces);
+}
+
 int mmpl_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                      const void* scale, int64_t mod_stride, int rows_per_frame, void* stream) {
   COUNTED(ln_modulate(x, ldx, out, ldo, S, D, eps, shift, scale, mod_stride, rows_per_frame,

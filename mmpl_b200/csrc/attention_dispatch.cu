@@ -18,6 +18,12 @@ namespace mmpl {
   }
 MMPL_DECLARE_ATTN_IMPL(prod)
 MMPL_DECLARE_ATTN_IMPL(half)
+namespace prod {
+int attn_plan_pieces(int Lq, int H, int kv_tiles, int ctas, int force_split, int* sched, int* pieces, int max_pieces);
+}
+int flash_attn_plan(int Lq, int H, int kv_tiles, int ctas, int force_split, int* sched, int* pieces, int max_pieces) {
+  return prod::attn_plan_pieces(Lq, H, kv_tiles, ctas, force_split, sched, pieces, max_pieces);
+}
 
 static int g_force_split = 0;
 void flash_attn_force_split(int split) { g_force_split = split; }

@@ -146,15 +146,15 @@ struct RangeGroup {
   int heads, units;     // heads and units in this group (units: only those the range schedule covers)
   int first_unit;       // global index of the group's first ranged unit
   int W;                // KV-tile units in this group = units * T  (host guarantees W * (G + 1) < 2^31)
-  __device__ __forceinline__ void set(const AttnParams& p, int g) {
-    heads = min(p.hg, p.H - g * p.hg);
+  __host__ __device__ __forceinline__ void set(const AttnParams& p, int g) {
+    heads = p.hg < p.H - g * p.hg ? p.hg : p.H - g * p.hg;
     first_unit = g * p.hg * p.QP + p.u_base;  // u_base > 0 only with a single group
     units = heads * p.QP - p.u_base;
     W = units * p.T;
   }
-  __device__ __forceinline__ int lo(int c, int G) const { return c * W / G; }
+  __host__ __device__ __forceinline__ int lo(int c, int G) const { return c * W / G; }
   // the CTA whose range contains position x: largest c with lo(c) <= x
-  __device__ __forceinline__ int cta_of(int x, int G) const { return ((x + 1) * G + W - 1) / W - 1; }
+  __host__ __device__ __forceinline__ int cta_of(int x, int G) const { return ((x + 1) * G + W - 1) / W - 1; }
 };
 
 struct PieceIter {
@@ -166,7 +166,7 @@ struct PieceIter {
   int pos, lo, hi;
   int wu;  // hybrid: next whole unit of this CTA
   RangeGroup grp;
-  __device__ __forceinline__ void init(const AttnParams& p, int cta, int grid) {
+  __host__ __device__ __forceinline__ void init(const AttnParams& p, int cta, int grid) {
     G = grid;
     c = cta;
     pi = cta;
@@ -175,7 +175,7 @@ struct PieceIter {
     ngroups = p.hg > 0 ? (p.H + p.hg - 1) / p.hg : 0;
     pos = hi = lo = 0;
   }
-  __device__ __forceinline__ bool next(const AttnParams& p, Piece& pc) {
+  __host__ __device__ __forceinline__ bool next(const AttnParams& p, Piece& pc) {
     if (p.hg == 0) {
       if (pi >= p.n_pieces) return false;
       const int per_head = p.split * p.QP;
@@ -212,7 +212,7 @@ struct PieceIter {
     pc.head = u / p.QP;
     pc.q_row0 = (u - pc.head * p.QP) * (2 * kQTile);
     pc.t0 = pos - ul * p.T;
-    const int end = min(hi, (ul + 1) * p.T);
+    const int end = hi < (ul + 1) * p.T ? hi : (ul + 1) * p.T;
     pc.n = end - pos;
     pc.whole = pc.n == p.T;
     pc.slot = (g * G + c) * 2 + (pos == lo ? 0 : 1);
@@ -226,7 +226,7 @@ struct PieceIter {
 struct UnitPieces {
   int np, u, c_first, g, start;
   RangeGroup grp;
-  __device__ __forceinline__ void init(const AttnParams& p, int unit) {
+  __host__ __device__ __forceinline__ void init(const AttnParams& p, int unit) {
     u = unit;
     c_first = g = start = 0;
     if (p.hg == 0) {
@@ -239,15 +239,15 @@ struct UnitPieces {
       np = grp.cta_of(start + p.T - 1, p.G) - c_first + 1;
     }
   }
-  __device__ __forceinline__ int slot(const AttnParams& p, int i) const {
+  __host__ __device__ __forceinline__ int slot(const AttnParams& p, int i) const {
     if (p.hg == 0) return u * p.split + i;
     const int c = c_first + i;
     const int lo = grp.lo(c, p.G);
     if (grp.lo(c + 1, p.G) <= lo) return -1;
-    return (g * p.G + c) * 2 + (max(lo, start) == lo ? 0 : 1);  // does the piece open its CTA's range?
+    return (g * p.G + c) * 2 + (lo >= start ? 0 : 1);  // does the piece open its CTA's range?
   }
   // pieces that really exist (the arrival count that makes a piece the last one)
-  __device__ __forceinline__ int count(const AttnParams& p) const {
+  __host__ __device__ __forceinline__ int count(const AttnParams& p) const {
     if (p.hg == 0) return np;
     int n = 0;
     for (int i = 0; i < np; ++i) n += slot(p, i) >= 0 ? 1 : 0;
@@ -967,6 +967,99 @@ attn_combine_kernel(const AttnParams p) {
   *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(q_row) * p.ldo + head * kHD + lane * 4) = w2;
 }
 
+// Work partition of one launch (host): fills the schedule fields of `p` (QP, T, split, n_pieces, hg, u_base) for Lq, H
+// already set, and returns the grid size G and the number of workspace slots for partial pieces. `sms` = CTAs of the
+// persistent grid (the SM count; smaller in tests). Pure host arithmetic: also reachable without a GPU through
+// attn_plan_pieces() / mmpl_attn_plan(), which the CPU test-suite uses to check that every (unit, KV tile) pair is
+// covered exactly once and that the merge bookkeeping (UnitPieces) agrees with the pieces the CTAs run.
+static void plan_schedule(AttnParams& p, int T, int sms, int force_split, int& G, size_t& slots) {
+  const int Lq = p.Lq, H = p.H;
+  // work partition: U units of T KV tiles over G persistent CTAs, by one of the two schedules of PieceIter.
+  // Cost model (in KV-tile times per SM; measured on B200 with tools/bench_kernels.py): a piece costs ~6 tile times on
+  // top of its tiles (Q load, pipeline fill, epilogue); merging costs 2 x 128 KB of traffic per partial piece ~ 0.029
+  // tile times each.
+  p.QP = (Lq + kUnitRows - 1) / kUnitRows;
+  p.T = T;
+  const int U = p.QP * H;
+  const double piece_fixed = 6.0, merge_per_piece = 0.0291, merge_fixed = 6.0;  // merge_fixed: the combine launch itself
+  int best_split = 1;
+  double best = 1e30;
+  for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
+    if (sp > 1 && T / sp < 8) break;
+    const int rounds = (U * sp + sms - 1) / sms;
+    const double cost = rounds * (static_cast<double>(T) / sp + piece_fixed) + (sp > 1 ? merge_fixed + merge_per_piece * U * sp : 0.0);
+    if (cost < best - 1e-9) { best = cost; best_split = sp; }
+  }
+  // Range schedule. Its CTAs sit at different KV positions of the same head, so (unlike the uniform schedule, whose
+  // CTAs stream the same K/V tiles in lockstep and are served by L2 together) it pays only while the K/V of all heads
+  // stays L2-resident: measured on B200 (profiles/README.md) 6 % faster than the best uniform split for L_kv = 9360
+  // and 14040 at cfg2 (58 / 86 MB of K/V), slower from 115 MB up, erratic with several head groups. Hence: one group
+  // of all heads, only below the L2 budget, and only when the cost model prefers it.
+  int hg = 0, u_base = 0;
+  {
+    static const int l2_mb = getenv("MMPL_ATTN_L2_MB") ? atoi(getenv("MMPL_ATTN_L2_MB")) : 90;
+    static const int mode_env = getenv("MMPL_ATTN_RANGES") ? atoi(getenv("MMPL_ATTN_RANGES")) : -1;  // 0 never, 1 whenever possible, -1 cost model
+    static const int hybrid_env = getenv("MMPL_ATTN_HYBRID") ? atoi(getenv("MMPL_ATTN_HYBRID")) : -1;  // same
+    const double head_mb = static_cast<double>(T) * kKVTile * 512.0 / (1 << 20);
+    const double kv_mb = H * head_mb;
+    const double pieces_per_cta = static_cast<double>(U) / sms + 1.0;
+    const double cost_ranges = static_cast<double>(U) * T / sms + piece_fixed * pieces_per_cta + merge_fixed + merge_per_piece * 2.0 * sms;
+    const bool fits32 = static_cast<long long>(U) * T * (sms + 1) < (1ll << 31);  // PieceIter's range arithmetic is 32-bit
+    const bool possible = T >= 16 && static_cast<long long>(U) * T >= 8ll * sms && kv_mb <= l2_mb && fits32;
+    if (possible && (mode_env == 1 || (mode_env < 0 && cost_ranges < best))) { hg = H; best = cost_ranges; }
+    // Hybrid schedule: floor(U/G) rounds of whole units in lockstep, the remaining U mod G units as ranges (merged in
+    // the kernel). Same tile count per CTA as the pure range schedule, but only the heads of the ranged units are read
+    // by free-running CTAs, so it stays inside L2 where the pure range schedule does not (cfg2 at L_kv = 32760: 5 of
+    // 12 heads, 84 MB), and it has no merge kernel, which the uniform split pays for (37 us per launch there).
+    const int rounds = U / sms, rem = U - rounds * sms;
+    if (rounds >= 1 && rem > 0) {
+      const int heads2 = H - (rounds * sms) / p.QP;  // heads the ranged units belong to
+      const double cost_hybrid = static_cast<double>(U) * T / sms + piece_fixed * (rounds + 2.0);
+      const bool hybrid_possible = T >= 16 && static_cast<long long>(rem) * T >= 6ll * sms && heads2 * head_mb <= l2_mb && fits32;
+      if (hybrid_possible && (hybrid_env == 1 || (hybrid_env < 0 && cost_hybrid < best))) {
+        hg = H;
+        u_base = rounds * sms;
+        best = cost_hybrid;
+      }
+    }
+  }
+  if (force_split > 0 && force_split <= T) {
+    best_split = force_split;
+    hg = 0;
+    u_base = 0;
+  } else if (force_split <= -1000) {
+    // test hook: hybrid schedule whenever there is at least one whole round and something left over
+    const int rounds = U / sms, rem = U - rounds * sms;
+    hg = 0;
+    u_base = 0;
+    if (rounds >= 1 && rem > 0 && static_cast<long long>(rem) * T >= 2ll * sms &&
+        static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
+      hg = H;
+      u_base = rounds * sms;
+    }
+  } else if (force_split < 0 && T >= 2 && static_cast<long long>(U) * T >= 2ll * sms &&
+             static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
+    hg = -force_split < H ? -force_split : H;  // test hook: range schedule with this many heads per group
+    u_base = 0;
+  }
+  static const bool nonpersistent = getenv("MMPL_ATTN_NONPERSISTENT") != nullptr;
+  slots = 0;
+  if (hg > 0) {
+    p.hg = hg;
+    p.u_base = u_base;
+    p.split = 1;
+    p.n_pieces = 0;
+    G = sms;
+    slots = static_cast<size_t>((H + hg - 1) / hg) * G * 2;
+  } else {
+    p.hg = 0;
+    p.split = best_split;
+    p.n_pieces = U * p.split;
+    G = (p.n_pieces < sms || nonpersistent) ? p.n_pieces : sms;
+    slots = p.split > 1 ? static_cast<size_t>(U) * p.split : 0;
+  }
+}
+
 // Workspace for partial pieces (grown on demand; one per process, used by launches on one stream at a time) and the
 // arrival counters of the in-kernel merge (zero between launches: the last piece of a unit clears its counter).
 static float* g_part = nullptr;
@@ -1009,97 +1102,11 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   const CUtensorMap* mv1 = uses1 ? get_tensor_map_bf16(v1, rows1, static_cast<uint64_t>(H) * kHD, ldkv1, 128) : mv0;
   if (!mq || !mk0 || !mv0 || !mk1 || !mv1) return MMPL_ERR_CUDA;
 
-  // work partition: U units of T KV tiles over G persistent CTAs, by one of the two schedules of PieceIter.
-  // Cost model (in KV-tile times per SM; measured on B200 with tools/bench_kernels.py): a piece costs ~6 tile times on
-  // top of its tiles (Q load, pipeline fill, epilogue); merging costs 2 x 128 KB of traffic per partial piece ~ 0.029
-  // tile times each.
-  p.QP = (Lq + kUnitRows - 1) / kUnitRows;
-  p.T = T;
-  const int U = p.QP * H;
-  const int sms = (force_ctas > 0 && force_ctas < sm_count()) ? force_ctas : sm_count();  // CTAs of the persistent grid
-  const double piece_fixed = 6.0, merge_per_piece = 0.0291, merge_fixed = 6.0;  // merge_fixed: the combine launch itself
-  int best_split = 1;
-  double best = 1e30;
-  for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
-    if (sp > 1 && T / sp < 8) break;
-    const int rounds = (U * sp + sms - 1) / sms;
-    const double cost = rounds * (static_cast<double>(T) / sp + piece_fixed) + (sp > 1 ? merge_fixed + merge_per_piece * U * sp : 0.0);
-    if (cost < best - 1e-9) { best = cost; best_split = sp; }
-  }
-  // Range schedule. Its CTAs sit at different KV positions of the same head, so (unlike the uniform schedule, whose
-  // CTAs stream the same K/V tiles in lockstep and are served by L2 together) it pays only while the K/V of all heads
-  // stays L2-resident: measured on B200 (profiles/README.md) 6 % faster than the best uniform split for L_kv = 9360
-  // and 14040 at cfg2 (58 / 86 MB of K/V), slower from 115 MB up, erratic with several head groups. Hence: one group
-  // of all heads, only below the L2 budget, and only when the cost model prefers it.
-  int hg = 0, u_base = 0;
-  {
-    static const int l2_mb = getenv("MMPL_ATTN_L2_MB") ? atoi(getenv("MMPL_ATTN_L2_MB")) : 90;
-    static const int mode_env = getenv("MMPL_ATTN_RANGES") ? atoi(getenv("MMPL_ATTN_RANGES")) : -1;  // 0 never, 1 whenever possible, -1 cost model
-    static const int hybrid_env = getenv("MMPL_ATTN_HYBRID") ? atoi(getenv("MMPL_ATTN_HYBRID")) : -1;  // same
-    const double head_mb = static_cast<double>(T) * kKVTile * 512.0 / (1 << 20);
-    const double kv_mb = H * head_mb;
-    const double pieces_per_cta = static_cast<double>(U) / sms + 1.0;
-    const double cost_ranges = static_cast<double>(U) * T / sms + piece_fixed * pieces_per_cta + merge_fixed + merge_per_piece * 2.0 * sms;
-    const bool fits32 = static_cast<long long>(U) * T * (sms + 1) < (1ll << 31);  // PieceIter's range arithmetic is 32-bit
-    const bool possible = T >= 16 && static_cast<long long>(U) * T >= 8ll * sms && kv_mb <= l2_mb && fits32;
-    if (possible && (mode_env == 1 || (mode_env < 0 && cost_ranges < best))) { hg = H; best = cost_ranges; }
-    // Hybrid schedule: floor(U/G) rounds of whole units in lockstep, the remaining U mod G units as ranges (merged in
-    // the kernel). Same tile count per CTA as the pure range schedule, but only the heads of the ranged units are read
-    // by free-running CTAs, so it stays inside L2 where the pure range schedule does not (cfg2 at L_kv = 32760: 5 of
-    // 12 heads, 84 MB), and it has no merge kernel, which the uniform split pays for (37 us per launch there).
-    const int rounds = U / sms, rem = U - rounds * sms;
-    if (rounds >= 1 && rem > 0) {
-      const int heads2 = H - (rounds * sms) / p.QP;  // heads the ranged units belong to
-      const double cost_hybrid = static_cast<double>(U) * T / sms + piece_fixed * (rounds + 2.0);
-      const bool hybrid_possible = T >= 16 && static_cast<long long>(rem) * T >= 6ll * sms && heads2 * head_mb <= l2_mb && fits32;
-      // (while the K/V of all heads is small against L2 the pure range schedule is as good or better — measured 129 vs
-      //  136 us at L_kv = 4680, level at 9360: its merges are spread over the kernel instead of all at the tail)
-      static const int ranges_mb = getenv("MMPL_ATTN_RANGES_MB") ? atoi(getenv("MMPL_ATTN_RANGES_MB")) : 45;
-      const bool ranges_better = hg > 0 && kv_mb <= ranges_mb;
-      if (hybrid_possible && (hybrid_env == 1 || (hybrid_env < 0 && cost_hybrid < best && !ranges_better))) {
-        hg = H;
-        u_base = rounds * sms;
-        best = cost_hybrid;
-      }
-    }
-  }
-  if (force_split > 0 && force_split <= T) {
-    best_split = force_split;
-    hg = 0;
-    u_base = 0;
-  } else if (force_split <= -1000) {
-    // test hook: hybrid schedule whenever there is at least one whole round and something left over
-    const int rounds = U / sms, rem = U - rounds * sms;
-    hg = 0;
-    u_base = 0;
-    if (rounds >= 1 && rem > 0 && static_cast<long long>(rem) * T >= 2ll * sms &&
-        static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
-      hg = H;
-      u_base = rounds * sms;
-    }
-  } else if (force_split < 0 && T >= 2 && static_cast<long long>(U) * T >= 2ll * sms &&
-             static_cast<long long>(U) * T * (sms + 1) < (1ll << 31)) {
-    hg = -force_split < H ? -force_split : H;  // test hook: range schedule with this many heads per group
-    u_base = 0;
-  }
-  static const bool nonpersistent = getenv("MMPL_ATTN_NONPERSISTENT") != nullptr;
-  int G;
+  int G = 0;
   size_t slots = 0;
-  if (hg > 0) {
-    p.hg = hg;
-    p.u_base = u_base;
-    p.split = 1;
-    p.n_pieces = 0;
-    G = sms;
-    slots = static_cast<size_t>((H + hg - 1) / hg) * G * 2;
-  } else {
-    p.hg = 0;
-    p.split = best_split;
-    p.n_pieces = U * p.split;
-    G = (p.n_pieces < sms || nonpersistent) ? p.n_pieces : sms;
-    slots = p.split > 1 ? static_cast<size_t>(U) * p.split : 0;
-  }
+  plan_schedule(p, T, (force_ctas > 0 && force_ctas < sm_count()) ? force_ctas : sm_count(), force_split, G, slots);
   p.G = G;
+  const int U = p.QP * H;
   if (slots > 0) {
     const size_t need = slots * kUnitRows * (kHD + 2) * sizeof(float);
     if (need > g_part_bytes) {
@@ -1117,7 +1124,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
     // time the last chunk is done and the in-kernel merge stalls that CTA's softmax warps on HBM reads (10-25 % slower
     // at L_kv >= 18720): attn_combine_kernel. MMPL_ATTN_MERGE=inline|kernel forces one for both (tests, A/B).
     static const char* merge_env = getenv("MMPL_ATTN_MERGE");
-    const bool merge_in_kernel = merge_env ? merge_env[0] == 'i' : hg > 0;
+    const bool merge_in_kernel = merge_env ? merge_env[0] == 'i' : p.hg > 0;
     if (merge_in_kernel) {
       const size_t need_cnt = static_cast<size_t>(U) * 2;
       if (need_cnt > g_merge_cnt_n) {
@@ -1145,6 +1152,54 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
   }
   return MMPL_OK;
 }
+
+#ifdef MMPL_ATTN_PROD
+// Host-only: the pieces every CTA of a launch would run, in order (no GPU needed). rows of `pieces`:
+// {cta, head, q_row0, t0, n, whole, slot, unit_pieces, merge_ok}: unit_pieces = how many pieces UnitPieces (the merge
+// bookkeeping) says the piece's unit has, merge_ok = 1 if this piece's slot is among the slots UnitPieces enumerates
+// for the unit (always 1 for whole pieces). Returns the number of pieces, or -1 if `max_pieces` is too small.
+int attn_plan_pieces(int Lq, int H, int kv_tiles, int ctas, int force_split, int* sched, int* pieces, int max_pieces) {
+  AttnParams p{};
+  p.Lq = Lq;
+  p.H = H;
+  int G = 0;
+  size_t slots = 0;
+  plan_schedule(p, kv_tiles, ctas, force_split, G, slots);
+  p.G = G;
+  if (sched) {
+    sched[0] = p.hg == 0 ? 0 : (p.u_base > 0 ? 2 : 1);  // 0 uniform split, 1 ranges, 2 hybrid
+    sched[1] = p.split;
+    sched[2] = p.hg;
+    sched[3] = p.u_base;
+    sched[4] = G;
+    sched[5] = static_cast<int>(slots);
+    sched[6] = p.QP;
+  }
+  int n = 0;
+  for (int c = 0; c < G; ++c) {
+    PieceIter it;
+    it.init(p, c, G);
+    Piece pc;
+    while (it.next(p, pc)) {
+      if (n >= max_pieces) return -1;
+      int np = 1, ok = 1;
+      if (!pc.whole) {
+        const int u = pc.head * p.QP + pc.q_row0 / kUnitRows;
+        UnitPieces up;
+        up.init(p, u);
+        np = up.count(p);
+        ok = 0;
+        for (int i = 0; i < up.np; ++i) ok |= (up.slot(p, i) == pc.slot) ? 1 : 0;
+      }
+      int* r = pieces + static_cast<size_t>(n) * 9;
+      r[0] = c; r[1] = pc.head; r[2] = pc.q_row0; r[3] = pc.t0; r[4] = pc.n; r[5] = pc.whole ? 1 : 0; r[6] = pc.slot;
+      r[7] = np; r[8] = ok;
+      ++n;
+    }
+  }
+  return n;
+}
+#endif
 
 #if MMPL_ATTN_TIMING
 extern "C" int mmpl_attn_debug_read(long long* out32, int reset) {

@@ -18,6 +18,8 @@ int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
 
 void flash_attn_force_split(int split);
 void flash_attn_force_ctas(int ctas);
+// host-only enumeration of a launch's work partition (see attention_tcgen05.cu: attn_plan_pieces)
+int flash_attn_plan(int Lq, int H, int kv_tiles, int ctas, int force_split, int* sched, int* pieces, int max_pieces);
 
 int ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int S, int D, float eps, const void* shift,
                 const void* scale, int64_t mod_stride, int rows_per_frame, cudaStream_t st);
