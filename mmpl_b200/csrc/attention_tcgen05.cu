@@ -41,8 +41,9 @@
 // attention_tcgen05_half.cu): S is produced, exponentiated and consumed in two independent 64-column halves, which
 // shortens the S -> P -> P.V -> next S round trip. Measured on B200 (profiles/r01_microbench_attention_halftile.txt):
 // the half-tile pipeline is 22 % faster for the 4-tile cross-attention (23.6 vs 30.2 us) and 0-6 % slower for the
-// long self-attention ranges (twice the barriers, fences and N=64 MMAs per tile), so the dispatcher
-// (attention_dispatch.cu) uses it for short KV ranges only.
+// long self-attention ranges (twice the barriers, fences and N=64 MMAs per tile), and inside the cfg2 step the
+// cross-attention gain does not show (972.4 vs 974.1 ms per step): opt-in through the dispatcher
+// (attention_dispatch.cu: MMPL_ATTN_HALF / MMPL_ATTN_HALF_TILES), the whole-tile build is the default everywhere.
 #ifndef MMPL_ATTN_SPLIT_S
 #define MMPL_ATTN_SPLIT_S 0
 #endif

@@ -227,7 +227,7 @@ def test_flash_attn_hybrid_schedule(Lq, Lk, H, ctas):
 @pytest.mark.parametrize("half", [0, 1])
 def test_flash_attn_both_pipelines_variant(half):
     """The library holds two builds of flash_attn_kernel (attention_tcgen05.cu: MMPL_ATTN_SPLIT_S): the whole-tile S
-    hand-over and the half-tile S pipeline; the dispatcher picks by KV length (half-tile for <= 8 KV tiles per unit).
+    hand-over (the default) and the half-tile S pipeline (opt-in).
     MMPL_ATTN_HALF=0|1 forces one for every call (read once per process, hence the subprocess): every attention test of
     this file - all shapes, forced splits, range and hybrid schedules, segments, lazy rescale - must pass with either."""
     import os
