@@ -56,6 +56,21 @@ int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
                    int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
                    const void* gate, int64_t gate_stride, int rows_per_frame, int tile_n, void* stream);
 
+/* Causal 3-D convolution, stride 1, channels-last, as a tap-GEMM on the tensor cores: replaces CausalConv3d.forward
+ * (wan/modules/vae.py:16-36: F.pad with all temporal padding in front + nn.Conv3d) and, with KT = 1, the per-frame
+ * nn.Conv2d(3x3, padding 1) / 1x1 convolutions of the same file (:75-81, :233-235) -- the contraction that carries the
+ * VAE "segment connect" either side of the anchor hand-off (Wan_fps_inference_parallel_4gpu_20s.py:191-205;
+ * SURVEY.md 8(f) row 2). Layouts (bf16):
+ *   in       [(T + KT - 1)][H + 2][W + 2][Cin]  one-pixel zero halo; the KT - 1 leading frames are the causal history
+ *                                               (zeros, or the frames `feat_cache` carries between chunks, vae.py:197-209)
+ *   w_packed [Cout][KT*KH*KW][Cin64]            Cin64 = Cin rounded up to a multiple of 64, zero padded; taps ordered
+ *                                               dt, dh, dw (= weight.permute(0,2,3,4,1) of the reference parameter)
+ *   bias     [Cout] or NULL;  residual: NULL or a tensor laid out like `out` (ResidualBlock's `x + h`, vae.py:213)
+ *   out      [T][H + 2][W + 2][Cout]            only interior positions are written: a zeroed buffer keeps its halo
+ * Cin and Cout must be multiples of 8 (pad channels in the layout); KT, KH = KW in {1, 3}. */
+int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
+                   int W, int Cin, int Cout, int KT, int KH, int KW, void* stream);
+
 /* Non-causal softmax(Q K^T * scale) V, head_dim 128; replaces flash_attention()/attention()
  * (wan/modules/attention.py:32-185). q: [Lq, H, 128] with row pitch ldq, out likewise with ldo.
  * KV source 0 (k0,v0: [rows0, H, 128], pitch ldkv0) and optional source 1 are read in place through

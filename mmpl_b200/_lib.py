@@ -46,6 +46,8 @@ SIGNATURES = {
     "mmpl_last_error": (C.c_char_p, []),
     "mmpl_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "mmpl_conv3d_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_void_p]),
     "mmpl_flash_attn": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_int64, c_float, c_void_p]),
     "mmpl_gemm_set_streamk": (c_int, [c_int]),

@@ -121,6 +121,11 @@ int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
                    rows_per_frame, tile_n, static_cast<cudaStream_t>(stream)));
 }
 
+int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
+                   int W, int Cin, int Cout, int KT, int KH, int KW, void* stream) {
+  COUNTED(conv3d_cl(in, w_packed, bias, out, residual, T, H, W, Cin, Cout, KT, KH, KW, static_cast<cudaStream_t>(stream)));
+}
+
 int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0, int64_t ldkv0,
                     int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1, int nseg,
                     const int* seg_start, const int* seg_rows, const int* seg_src, void* out, int64_t ldo,

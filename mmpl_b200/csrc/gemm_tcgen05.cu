@@ -44,6 +44,13 @@ struct GemmParams {
   int group_m;         // tile order of the pair kernel: groups of group_m tile rows, row-fastest inside a group
   float* sk_part;      // [pairs][2 CTAs][128 rows][256 columns] fp32 partial accumulators
   uint32_t* sk_flags;  // [pairs][2 CTAs]: 1 = the partial of this CTA's head segment is in sk_part
+  // Tap-GEMM convolution (CONV instantiations of the single-CTA kernel only, see conv3d_cl): the K axis is
+  // taps x channel blocks; k block kb reads channel block kb % conv_kb_per_tap of the A rows shifted by
+  // conv_tap_off[kb / conv_kb_per_tap]; only rows that are interior positions of the padded [.., conv_hp, conv_wp] grid
+  // are stored.
+  int conv_kb_per_tap;
+  int conv_hp, conv_wp;
+  int conv_tap_off[27];
 };
 
 template <int BN>
@@ -70,12 +77,18 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // thread owns output row `row`, columns [col_base, col_base + BN). Rounds to bf16 where the reference does.
 // `part` (stream-K owner segments only): `nparts` fp32 partial accumulator rows of this thread's row, `part_stride`
 // floats apart, written by other CTAs; they are added to the TMEM accumulator before the epilogue arithmetic.
-template <int BN, int EPI>
+template <int BN, int EPI, bool CONV = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int col_base, int c_begin,
                                               int c_end, const float* part = nullptr, int nparts = 0,
                                               int64_t part_stride = 0) {
   constexpr bool kHasRes = (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES);
-  const bool row_ok = row < p.M;
+  bool row_ok = row < p.M;
+  if (CONV) {
+    // rows are positions of the zero-haloed grid: the halo stays zero (never written), interior rows are stored
+    const int wp = row % p.conv_wp;
+    const int hp = (row / p.conv_wp) % p.conv_hp;
+    row_ok = row_ok && wp >= 1 && wp < p.conv_wp - 1 && hp >= 1 && hp < p.conv_hp - 1;
+  }
   const __nv_bfloat16* gate_row = nullptr;
   if (EPI == MMPL_EPI_BIAS_GATE_RES && row_ok)
     gate_row = p.gate + static_cast<int64_t>(row / p.rows_per_frame) * p.gate_stride;
@@ -187,7 +200,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p) {
@@ -247,7 +260,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx_elect(&full_bar[s], Cfg::kStageBytes);
-        tma_load_2d_elect(smem_a + s * Cfg::kABytes, &map_a, &full_bar[s], kb * kBK, m_blk * kBM, kEvictNormal);
+        if (CONV) {
+          // tap-GEMM: the same 128 grid positions shifted by this tap's offset (negative / past-the-end rows and
+          // channels beyond Cin are zero-filled by TMA); W is packed [Cout][taps][Cin rounded up to 64]
+          const int tap = kb / p.conv_kb_per_tap;
+          const int cb = kb - tap * p.conv_kb_per_tap;
+          tma_load_2d_elect(smem_a + s * Cfg::kABytes, &map_a, &full_bar[s], cb * kBK, m_blk * kBM + p.conv_tap_off[tap],
+                            kEvictNormal);
+        } else {
+          tma_load_2d_elect(smem_a + s * Cfg::kABytes, &map_a, &full_bar[s], kb * kBK, m_blk * kBM, kEvictNormal);
+        }
         tma_load_2d_elect(smem_b + s * Cfg::kBBytes, &map_b, &full_bar[s], kb * kBK, n_blk * BN, kEvictLast);
         if (++s == ST) { s = 0; ph ^= 1; }
       }
@@ -295,8 +317,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int row = m_blk * kBM + lane_base + lane;
       constexpr int kChunks = BN / 32 / 2;  // 32-column chunks per warp
       const int half = (warp - 2) >> 2;
-      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
-                             half * kChunks, (half + 1) * kChunks);
+      epilogue_tile<BN, EPI, CONV>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
+                                   half * kChunks, (half + 1) * kChunks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -796,6 +818,80 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   if (bn == 256) return dispatch_epi<256>(epilogue, ma, mb, p, stream);
   if (bn == 128) return dispatch_epi<128>(epilogue, ma, mb, p, stream);
   return dispatch_epi<64>(epilogue, ma, mb, p, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Causal 3-D convolution as a tap-GEMM (wan/modules/vae.py:16-36 CausalConv3d, stride 1; also its per-frame Conv2d
+// 3x3 and the 1x1 convolutions), channels-last:
+//   in  [(T + KT - 1)][H + 2][W + 2][Cin]   bf16, zero halo of one pixel; the KT-1 leading frames are the causal
+//                                            history (zeros for the first chunk, carried frames otherwise)
+//   w   [Cout][KT * KH * KW][Cin64]          bf16, Cin64 = Cin rounded up to 64 (zero padded), taps dt-major
+//   out [T][H + 2][W + 2][Cout]              bf16; interior positions only are written
+// out(t, h, w, :) = bias + sum_taps in(t + dt, h + dh - KH/2, w + dw - KW/2, :) . w[:, tap, :]  (+ residual)
+// Every grid position (halo included) is one GEMM row; a tap is a row shift of the same A matrix, so the A operand
+// is read in place by TMA: no im2col buffer. The halo rows cost (H+2)(W+2)/(HW) - 1 extra MMA work (0.7 % at 480x832).
+template <int BN, int EPI>
+static int launch_conv(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, EPI, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + kBM - 1) / kBM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  MMPL_CUDA_LAUNCH(launch_kernel(kern, grid, kGemmThreads, Cfg::kSmemBytes, stream, *ma, *mb, p));
+  MMPL_CUDA(cudaGetLastError());
+  return MMPL_OK;
+}
+
+int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
+              int W, int Cin, int Cout, int KT, int KH, int KW, cudaStream_t stream) {
+  MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "conv3d: requires an sm_100 device");
+  MMPL_CHECK(in && w_packed && out, MMPL_ERR_ARG, "conv3d: null argument");
+  MMPL_CHECK(T > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, MMPL_ERR_SHAPE, "conv3d: bad shape");
+  MMPL_CHECK(Cin % 8 == 0 && Cout % 8 == 0, MMPL_ERR_SHAPE,
+             "conv3d: channel counts must be multiples of 8 (pad the layout): Cin=%d Cout=%d", Cin, Cout);
+  MMPL_CHECK((KT == 1 || KT == 3) && (KH == 1 || KH == 3) && KH == KW, MMPL_ERR_SHAPE,
+             "conv3d: kernel %dx%dx%d not supported (1 or 3 per axis, square)", KT, KH, KW);
+  const int Hp = H + 2, Wp = W + 2;
+  const int64_t rows_out = static_cast<int64_t>(T) * Hp * Wp;
+  const int64_t rows_in = static_cast<int64_t>(T + KT - 1) * Hp * Wp;
+  MMPL_CHECK(rows_in < (int64_t(1) << 31) - 65536, MMPL_ERR_SHAPE, "conv3d: %lld grid positions exceed the 32-bit row index",
+             (long long)rows_in);
+  const int taps = KT * KH * KW;
+  const int kb_per_tap = (Cin + kBK - 1) / kBK;
+  const int cin64 = kb_per_tap * kBK;
+
+  GemmParams p{};
+  p.M = static_cast<int>(rows_out);
+  p.N = Cout;
+  p.K = taps * cin64;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = Cout;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.res = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = Cout;
+  p.rows_per_frame = 1;
+  p.conv_kb_per_tap = kb_per_tap;
+  p.conv_hp = Hp;
+  p.conv_wp = Wp;
+  int i = 0;
+  for (int dt = 0; dt < KT; ++dt)
+    for (int dh = 0; dh < KH; ++dh)
+      for (int dw = 0; dw < KW; ++dw) p.conv_tap_off[i++] = (dt * Hp + (dh - KH / 2)) * Wp + (dw - KW / 2);
+
+  const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : ((Cout <= 256 || Cout % 256 == 0) ? 256 : 128));
+  const CUtensorMap* ma = get_tensor_map_bf16(in, static_cast<uint64_t>(rows_in), Cin, Cin, kBM);
+  const CUtensorMap* mb = get_tensor_map_bf16(w_packed, Cout, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.K), bn);
+  if (!ma || !mb) return MMPL_ERR_CUDA;
+  const bool res = residual != nullptr;
+  if (bn == 256) return res ? launch_conv<256, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<256, MMPL_EPI_BIAS>(ma, mb, p, stream);
+  if (bn == 128) return res ? launch_conv<128, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<128, MMPL_EPI_BIAS>(ma, mb, p, stream);
+  return res ? launch_conv<64, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<64, MMPL_EPI_BIAS>(ma, mb, p, stream);
 }
 
 }  // namespace mmpl

@@ -9,6 +9,10 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
               int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
               const void* gate, int64_t gate_stride, int rows_per_frame, int force_bn, cudaStream_t stream);
 
+// Causal 3-D convolution as a tap-GEMM over a zero-haloed channels-last grid (gemm_tcgen05.cu: conv3d_cl).
+int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
+              int W, int Cin, int Cout, int KT, int KH, int KW, cudaStream_t stream);
+
 void gemm_set_streamk(int mode);  // -1 automatic (default), 0 off, 1 forced
 
 int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,

@@ -202,3 +202,66 @@ def add_noise(x0: torch.Tensor, noise: torch.Tensor, sigma: torch.Tensor) -> tor
     _lib.check(lib.mmpl_add_noise(x0.data_ptr(), noise.data_ptr(), sigma.data_ptr(), out.data_ptr(), n,
                                   x0.numel() // n, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------ VAE segment connect
+
+def pack_conv_weight(weight: torch.Tensor) -> torch.Tensor:
+    """Reference conv parameter [Cout, Cin, KT, KH, KW] (or [Cout, Cin, KH, KW] of a per-frame Conv2d) -> the tap-major
+    layout mmpl_conv3d_cl reads: [Cout8, KT*KH*KW, Cin64] bf16, Cin zero-padded to a multiple of 64 and Cout to a
+    multiple of 8. One-time layout transform of the weights (no arithmetic)."""
+    if weight.dim() == 4:
+        weight = weight.unsqueeze(2)
+    cout, cin, kt, kh, kw = weight.shape
+    cin64, cout8 = -(-cin // 64) * 64, -(-cout // 8) * 8
+    w = weight.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh * kw, cin)
+    packed = torch.zeros((cout8, kt * kh * kw, cin64), dtype=torch.bfloat16, device=weight.device)
+    packed[:cout, :, :cin] = w.to(torch.bfloat16)
+    return packed
+
+
+def to_haloed(x: torch.Tensor, lead: int = 2, channels: Optional[int] = None) -> torch.Tensor:
+    """[C, T, H, W] -> channels-last grid [lead + T, H + 2, W + 2, C8] with a zero halo and `lead` zero frames in front
+    (the layout the VAE kernels keep their activations in; C padded to a multiple of 8 or to `channels`)."""
+    c, t, h, w = x.shape
+    c8 = channels if channels is not None else -(-c // 8) * 8
+    g = torch.zeros((lead + t, h + 2, w + 2, c8), dtype=torch.bfloat16, device=x.device)
+    g[lead:, 1:-1, 1:-1, :c] = x.permute(1, 2, 3, 0).to(torch.bfloat16)
+    return g
+
+
+def from_haloed(g: torch.Tensor, lead: int = 2, channels: Optional[int] = None) -> torch.Tensor:
+    """Inverse of to_haloed: [lead + T, H + 2, W + 2, C8] -> [C, T, H, W]."""
+    c = g.shape[3] if channels is None else channels
+    return g[lead:, 1:-1, 1:-1, :c].permute(3, 0, 1, 2).contiguous()
+
+
+def conv3d_causal_cl(grid: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], kernel: Sequence[int],
+                     lead: int = 2, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CausalConv3d.forward (wan/modules/vae.py:16-36), stride 1, on a haloed channels-last grid (see to_haloed).
+    `grid` holds `lead` >= KT-1 history frames in front of its T frames; the result is a grid of the same geometry
+    (same `lead`, history frames and halo zero) with Cout channels. `residual`: a grid like the result, added in the epilogue."""
+    lib = _lib.load()
+    _req(grid, "grid"); _req(w_packed, "w_packed")
+    kt, kh, kw = (int(k) for k in kernel)
+    frames, hp, wp, cin = grid.shape
+    t = frames - lead
+    cout = w_packed.shape[0]
+    if lead < kt - 1 or t <= 0:
+        raise ValueError(f"grid has {lead} leading frames, the kernel needs {kt - 1}")
+    if w_packed.shape[1] != kt * kh * kw or w_packed.shape[2] != -(-cin // 64) * 64:
+        raise ValueError("w_packed does not match the grid's channels / the kernel size (see pack_conv_weight)")
+    if out is None:
+        out = torch.zeros((frames, hp, wp, cout), dtype=torch.bfloat16, device=grid.device)
+    if bias is not None and bias.numel() != cout:
+        bias = torch.cat([bias.to(torch.bfloat16), bias.new_zeros(cout - bias.numel(), dtype=torch.bfloat16)])
+    frame = hp * wp
+    esz = 2
+    if bias is not None:
+        bias = bias.to(torch.bfloat16).contiguous()
+    _lib.check(lib.mmpl_conv3d_cl(
+        grid.data_ptr() + (lead - (kt - 1)) * frame * cin * esz, w_packed.data_ptr(), _p(bias),
+        out.data_ptr() + lead * frame * cout * esz,
+        None if residual is None else residual.data_ptr() + lead * frame * cout * esz,
+        t, hp - 2, wp - 2, cin, cout, kt, kh, kw, _stream()))
+    return out
