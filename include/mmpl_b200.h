@@ -71,6 +71,25 @@ int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
 int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
                    int W, int Cin, int Cout, int KT, int KH, int KW, void* stream);
 
+/* RMS_norm.forward (wan/modules/vae.py:39-55: F.normalize over channels * sqrt(C) * gamma), optionally followed by
+ * nn.SiLU (the `RMS_norm, SiLU` pairs of ResidualBlock / the heads, vae.py:180-186,309-311,413-415), over `rows` rows of C
+ * bf16 channels (any contiguous [rows, C] view of the haloed grid: zero rows stay zero). bf16 rounding after each of the
+ * reference's operators. C % 8 == 0, C <= 1024. out may alias x. */
+int mmpl_vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamma, int silu, void* stream);
+
+/* Upsample(scale_factor=(2,2), mode='nearest') of every frame (vae.py:58-64,75-78): in [frames][H+2][W+2][C] ->
+ * out [frames][2H+2][2W+2][C]; interior positions only are written (a zeroed `out` keeps its halo). */
+int mmpl_vae_upsample2x(const void* in, void* out, int frames, int H, int W, int C, void* stream);
+
+/* The stride-2 pick that turns a stride-1 3x3 "same" convolution of the haloed grid into the reference's
+ * nn.ZeroPad2d((0,1,0,1)) + nn.Conv2d(3, stride=(2,2)) (vae.py:85-88): out interior (i, j) = in interior (2i+1, 2j+1).
+ * in [frames][Hin+2][Win+2][C] -> out [frames][Hin/2+2][Win/2+2][C], interior only. */
+int mmpl_vae_pick_odd(const void* in, void* out, int frames, int Hin, int Win, int C, void* stream);
+
+/* p[r, :] = softmax(scale * s[r, :]) in fp32, bf16 in and out (row pitches lds / ldp in elements): the softmax of the
+ * single-head attention of AttentionBlock (vae.py:241-266), whose head dimension (384) is outside mmpl_flash_attn's. */
+int mmpl_softmax_rows(const void* s, int64_t lds, void* p, int64_t ldp, int rows, int L, float scale, void* stream);
+
 /* Non-causal softmax(Q K^T * scale) V, head_dim 128; replaces flash_attention()/attention()
  * (wan/modules/attention.py:32-185). q: [Lq, H, 128] with row pitch ldq, out likewise with ldo.
  * KV source 0 (k0,v0: [rows0, H, 128], pitch ldkv0) and optional source 1 are read in place through

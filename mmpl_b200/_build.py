@@ -19,7 +19,7 @@ REPO = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libmmpl_b200.so"
 OBJ_DIR = REPO / "build" / "obj"
 
-SOURCES = ["host_util.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention_tcgen05_half.cu", "attention_dispatch.cu", "pointwise.cu", "api.cu"]
+SOURCES = ["host_util.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention_tcgen05_half.cu", "attention_dispatch.cu", "pointwise.cu", "vae_pointwise.cu", "api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

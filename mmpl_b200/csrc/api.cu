@@ -126,6 +126,19 @@ int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void*
   COUNTED(conv3d_cl(in, w_packed, bias, out, residual, T, H, W, Cin, Cout, KT, KH, KW, static_cast<cudaStream_t>(stream)));
 }
 
+int mmpl_vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamma, int silu, void* stream) {
+  COUNTED(vae_norm_act(x, out, rows, C, gamma, silu, static_cast<cudaStream_t>(stream)));
+}
+int mmpl_vae_upsample2x(const void* in, void* out, int frames, int H, int W, int C, void* stream) {
+  COUNTED(vae_upsample2x(in, out, frames, H, W, C, static_cast<cudaStream_t>(stream)));
+}
+int mmpl_vae_pick_odd(const void* in, void* out, int frames, int Hin, int Win, int C, void* stream) {
+  COUNTED(vae_pick_odd(in, out, frames, Hin, Win, C, static_cast<cudaStream_t>(stream)));
+}
+int mmpl_softmax_rows(const void* s, int64_t lds, void* p, int64_t ldp, int rows, int L, float scale, void* stream) {
+  COUNTED(softmax_rows(s, lds, p, ldp, rows, L, scale, static_cast<cudaStream_t>(stream)));
+}
+
 int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0, int64_t ldkv0,
                     int rows0, const void* k1, const void* v1, int64_t ldkv1, int rows1, int nseg,
                     const int* seg_start, const int* seg_rows, const int* seg_src, void* out, int64_t ldo,

@@ -13,6 +13,12 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
 int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
               int W, int Cin, int Cout, int KT, int KH, int KW, cudaStream_t stream);
 
+// vae_pointwise.cu: HBM-bound kernels of the VAE segment connect on the zero-haloed channels-last grid
+int vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamma, int silu, cudaStream_t st);
+int vae_upsample2x(const void* in, void* out, int frames, int H, int W, int C, cudaStream_t st);
+int vae_pick_odd(const void* in, void* out, int frames, int Hin, int Win, int C, cudaStream_t st);
+int softmax_rows(const void* s, int64_t lds, void* p, int64_t ldp, int rows, int L, float scale, cudaStream_t st);
+
 void gemm_set_streamk(int mode);  // -1 automatic (default), 0 off, 1 forced
 
 int flash_attn_bf16(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0,

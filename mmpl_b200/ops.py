@@ -265,3 +265,49 @@ def conv3d_causal_cl(grid: torch.Tensor, w_packed: torch.Tensor, bias: Optional[
         None if residual is None else residual.data_ptr() + lead * frame * cout * esz,
         t, hp - 2, wp - 2, cin, cout, kt, kh, kw, _stream()))
     return out
+
+
+def vae_norm_act(grid: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RMS_norm (+ SiLU) over the channels of every grid position (wan/modules/vae.py:39-55). gamma: any shape with C elements."""
+    lib = _lib.load()
+    _req(grid, "grid")
+    if not grid.is_contiguous():
+        raise ValueError("grid must be contiguous")
+    c = grid.shape[-1]
+    g = gamma.reshape(-1).to(torch.bfloat16)
+    if g.numel() != c:  # channel-padded layouts: padded channels are zero and stay zero
+        g = torch.cat([g, g.new_ones(c - g.numel())])
+    if out is None:
+        out = torch.empty_like(grid)
+    _lib.check(lib.mmpl_vae_norm_act(grid.data_ptr(), out.data_ptr(), grid.numel() // c, c, g.data_ptr(), int(silu), _stream()))
+    return out
+
+
+def vae_upsample2x(grid: torch.Tensor) -> torch.Tensor:
+    """Nearest-neighbour 2x up-sampling of every frame of a haloed grid (vae.py:58-64)."""
+    lib = _lib.load()
+    _req(grid, "grid")
+    frames, hp, wp, c = grid.shape
+    out = torch.zeros((frames, 2 * (hp - 2) + 2, 2 * (wp - 2) + 2, c), dtype=torch.bfloat16, device=grid.device)
+    _lib.check(lib.mmpl_vae_upsample2x(grid.data_ptr(), out.data_ptr(), frames, hp - 2, wp - 2, c, _stream()))
+    return out
+
+
+def vae_pick_odd(grid: torch.Tensor) -> torch.Tensor:
+    """out interior (i, j) = in interior (2i+1, 2j+1): stride-1 "same" conv -> ZeroPad2d((0,1,0,1)) + stride-2 conv (vae.py:85-88)."""
+    lib = _lib.load()
+    _req(grid, "grid")
+    frames, hp, wp, c = grid.shape
+    out = torch.zeros((frames, (hp - 2) // 2 + 2, (wp - 2) // 2 + 2, c), dtype=torch.bfloat16, device=grid.device)
+    _lib.check(lib.mmpl_vae_pick_odd(grid.data_ptr(), out.data_ptr(), frames, hp - 2, wp - 2, c, _stream()))
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float) -> torch.Tensor:
+    """softmax(scale * s) over the last dimension of a 2-D bf16 tensor, fp32 inside."""
+    lib = _lib.load()
+    _req(s, "s")
+    p = torch.empty_like(s)
+    _lib.check(lib.mmpl_softmax_rows(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1],
+                                     float(scale), _stream()))
+    return p

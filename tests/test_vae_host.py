@@ -1,0 +1,155 @@
+"""CPU: the host orchestration of the VAE segment connect (mmpl_b200/vae.py) with every kernel replaced by a torch
+emulation of its C-ABI contract (include/mmpl_b200.h: same layouts, same bf16 rounding points), against the goldens
+recorded from the unmodified reference VAE. This pins everything the host side decides — layer order and state-dict
+names, the haloed-grid bookkeeping, the whole-sequence handling of the temporal up/down-samplers ('Rep' quirk, frame-0
+pass-through), the stride-2 picks, the attention plumbing and the causally reduced connect — independently of the GPU;
+the kernels themselves are checked against the oracle in tests/test_vae_gpu.py. The product never runs these emulations."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import vae_oracle as V  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden" / "vae_small.pt"
+BF = torch.bfloat16
+
+
+def _r(x):  # one bf16 rounding
+    return x.to(BF).float()
+
+
+# ---------------------------------------------------------------------------------- kernel contracts, emulated
+def emu_conv3d_causal_cl(grid, w_packed, bias, kernel, lead=2, residual=None, out=None):
+    """mmpl_conv3d_cl: every grid position is a GEMM row, a tap is a row shift (zero outside the tensor), interior stores."""
+    kt, kh, kw = kernel
+    frames, hp, wp, cin = grid.shape
+    t, cout = frames - lead, w_packed.shape[0]
+    a = grid.reshape(-1, cin).float()
+    base, rows_in, m = (lead - (kt - 1)) * hp * wp, (t + kt - 1) * hp * wp, t * hp * wp
+    acc = torch.zeros(m, cout)
+    r = torch.arange(m)
+    i = 0
+    for dt in range(kt):
+        for dh in range(kh):
+            for dw in range(kw):
+                idx = r + (dt * hp + (dh - kh // 2)) * wp + (dw - kw // 2)
+                ok = (idx >= 0) & (idx < rows_in)
+                rows = torch.zeros(m, cin)
+                rows[ok] = a[base + idx[ok]]
+                acc += rows @ w_packed[:, i, :cin].float().T
+                i += 1
+    if bias is not None:
+        b = bias.float().reshape(-1)
+        acc[:, :b.numel()] += b
+    y = _r(acc)
+    if residual is not None:
+        y = _r(residual.reshape(-1, cout)[lead * hp * wp:].float() + y)
+    res = torch.zeros(frames, hp, wp, cout, dtype=BF)
+    interior = ((r % wp) >= 1) & ((r % wp) < wp - 1) & (((r // wp) % hp) >= 1) & (((r // wp) % hp) < hp - 1)
+    res.reshape(-1, cout)[lead * hp * wp + r[interior]] = y[interior].to(BF)
+    return res
+
+
+def emu_vae_norm_act(grid, gamma, silu=True, out=None):
+    x = grid.float()
+    c = x.shape[-1]
+    g = gamma.reshape(-1).float()
+    if g.numel() != c:
+        g = torch.cat([g, torch.ones(c - g.numel())])
+    n = _r(x.pow(2).sum(-1, keepdim=True).sqrt()).clamp_min(1e-12)
+    y = _r(_r(_r(x / n) * torch.tensor(float(c)).sqrt()) * g)
+    if silu:
+        y = y / (1 + torch.exp(-y))
+    return y.to(BF)
+
+
+def emu_vae_upsample2x(grid):
+    frames, hp, wp, c = grid.shape
+    out = torch.zeros(frames, 2 * (hp - 2) + 2, 2 * (wp - 2) + 2, c, dtype=BF)
+    out[:, 1:-1, 1:-1] = grid[:, 1:-1, 1:-1].repeat_interleave(2, 1).repeat_interleave(2, 2)
+    return out
+
+
+def emu_vae_pick_odd(grid):
+    frames, hp, wp, c = grid.shape
+    h, w = (hp - 2) // 2, (wp - 2) // 2
+    out = torch.zeros(frames, h + 2, w + 2, c, dtype=BF)
+    out[:, 1:-1, 1:-1] = grid[:, 2:2 * h + 1:2, 2:2 * w + 1:2]
+    return out
+
+
+def emu_softmax_rows(s, scale):
+    return torch.softmax(s.float() * scale, dim=-1).to(BF)
+
+
+def emu_linear(x, weight, bias=None, *, epilogue=0, residual=None, **kw):
+    y = x.float() @ weight.float().T
+    if bias is not None:
+        y = y + bias.float()
+    y = _r(y)
+    if epilogue == 3:   # EPI_BIAS_RES
+        y = _r(residual.float() + y)
+    else:
+        assert epilogue == 0
+    return y.to(BF)
+
+
+@pytest.fixture()
+def vae(monkeypatch):
+    from mmpl_b200 import ops
+    from mmpl_b200.vae import WanVAEWrapper
+    for name, fn in (("conv3d_causal_cl", emu_conv3d_causal_cl), ("vae_norm_act", emu_vae_norm_act),
+                     ("vae_upsample2x", emu_vae_upsample2x), ("vae_pick_odd", emu_vae_pick_odd),
+                     ("softmax_rows", emu_softmax_rows), ("linear", emu_linear)):
+        monkeypatch.setattr(ops, name, fn)
+    m = WanVAEWrapper()
+    m.load_vae_state_dict(V.make_weights(V.VaeConfig(), 0, BF), device="cpu")
+    return m
+
+
+def inputs():  # oracle/make_golden_vae.py:inputs(bf16)
+    g = torch.Generator().manual_seed(7)
+    pixels = (torch.rand(1, 3, 9, 32, 48, generator=g) * 2 - 1).to(BF)
+    latents = torch.randn(1, 4, 16, 4, 6, generator=g).to(BF)
+    anchors = torch.randn(1, 8, 16, 4, 6, generator=g).to(BF)
+    return pixels, latents, anchors
+
+
+def _close(name, got, want, atol):
+    got, want = got.float(), want.float()
+    err = float((got - want).abs().max())
+    cos = float(F.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+    print(f"{name}: max_abs={err:.4g} cos={cos:.6f}")
+    assert got.shape == want.shape and err <= atol and cos >= 0.9995, f"{name}: max_abs {err}, cos {cos}"
+
+
+def test_decode_matches_reference_vae(vae):
+    g = torch.load(GOLDEN)["bf16"]
+    _close("decode", vae.decode_to_pixel(inputs()[1]), g["decode"], atol=0.06)
+
+
+def test_encode_matches_reference_vae(vae):
+    g = torch.load(GOLDEN)["bf16"]
+    _close("encode", vae.encode_to_latent(inputs()[0]), g["encode"], atol=0.06)
+
+
+def test_segment_connect_matches_reference_driver(vae):
+    g = torch.load(GOLDEN)["bf16"]
+    out = vae.segment_connect(inputs()[2])
+    assert out.dtype == BF
+    _close("connect", out, g["connect"], atol=0.08)
+
+
+def test_no_cpu_path():
+    """Without the emulations the wrapper goes to the sm_100a library and refuses CPU tensors."""
+    from mmpl_b200.vae import WanVAEWrapper
+    m = WanVAEWrapper()
+    m.load_vae_state_dict({k: v for k, v in V.make_weights(V.VaeConfig(), 0, BF).items() if k.startswith(("conv2", "decoder.conv1"))},
+                          device="cpu")
+    with pytest.raises((ValueError, RuntimeError)):
+        m.decode_to_pixel(inputs()[1])
