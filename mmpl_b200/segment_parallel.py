@@ -66,6 +66,12 @@ def default_segment_connect(anchors: torch.Tensor) -> torch.Tensor:
     return anchors[:, -2:].contiguous()
 
 
+def vae_segment_connect(vae) -> Callable[[torch.Tensor], torch.Tensor]:
+    """The reference's segment connect itself (decode the anchors, pixel frames 8:13, re-encode, first 2 latents) on the
+    hand-written VAE path: `vae` is a mmpl_b200.vae.WanVAEWrapper with weights bound. Pass as `connect=`."""
+    return lambda anchors: vae.segment_connect(anchors)
+
+
 class AnchorChannel:
     """Point-to-point hand-off of one segment's anchor latents to the rank that runs the next segment."""
 

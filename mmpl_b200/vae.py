@@ -3,7 +3,7 @@ segment's anchor latents before the next segment may start (Wan_fps_inference_pa
 decode 21 latent frames of which 4 are non-zero, keep pixel frames 8..12, re-encode, keep latents 0..1 — through the
 reference's wrapper interface (`WanVAEWrapper.decode_to_pixel` / `encode_to_latent`, utils/wan_wrapper.py:74-113).
 
-B200 design (DESIGN.md §9):
+B200 design (DESIGN.md §7):
 * activations never leave one layout: a zero-haloed channels-last grid `[2 + T, H + 2, W + 2, C]` bf16 (two leading zero
   frames = the causal padding; the halo = the spatial padding). Every convolution of the network — 3x3x3 causal,
   (3,1,1) temporal, per-frame 3x3, 1x1 — is one launch of the tap-GEMM tcgen05 kernel (`mmpl_conv3d_cl`) reading
@@ -80,8 +80,26 @@ class WanVAEWrapper(torch.nn.Module):
         self.dim, self.z_dim = dim, z_dim
         self.mean = torch.tensor(LATENT_MEAN[:z_dim], dtype=torch.float32)
         self.std = torch.tensor(LATENT_STD[:z_dim], dtype=torch.float32)
+        self._dim_mult = tuple(dim_mult)
         self._enc = _program("encoder", dim, dim_mult, num_res_blocks, temperal_downsample)
         self._dec = _program("decoder", dim, dim_mult, num_res_blocks, temperal_downsample)
+        # output channels of every residual block (vae.py:284-300, 384-405)
+        self._res_out: Dict[str, int] = {}
+        i = 0
+        for lvl, m in enumerate(dim_mult):
+            for _ in range(num_res_blocks):
+                self._res_out[f"encoder.downsamples.{i}"] = dim * m
+                i += 1
+            i += 1 if lvl != len(dim_mult) - 1 else 0
+        i = 0
+        for lvl, m in enumerate(list(dim_mult)[::-1]):
+            for _ in range(num_res_blocks + 1):
+                self._res_out[f"decoder.upsamples.{i}"] = dim * m
+                i += 1
+            i += 1 if lvl != len(dim_mult) - 1 else 0
+        for side in ("encoder", "decoder"):
+            for j in (0, 2):
+                self._res_out[f"{side}.middle.{j}"] = dim * dim_mult[-1]
         self._w: Dict[str, torch.Tensor] = {}      # packed conv weights / raw vectors, by state-dict name
         self._kernel: Dict[str, tuple] = {}        # conv name -> (kt, kh, kw)
 
@@ -103,6 +121,64 @@ class WanVAEWrapper(torch.nn.Module):
                     self._w[name] = ops.pack_conv_weight(t)
             else:
                 self._w[name] = t.reshape(-1).to(torch.bfloat16).contiguous()
+
+    def init_random_weights(self, seed: int = 0, device="cuda") -> Dict[str, torch.Tensor]:
+        """Synthetic stand-in for the absent Wan2.1_VAE.pth: seeded fan-in-scaled normals under the
+        reference's state-dict names and shapes, bound like a checkpoint. Returns the state dict."""
+        g = torch.Generator().manual_seed(seed)
+        sd: Dict[str, torch.Tensor] = {}
+
+        def conv(name, cout, cin, *k):
+            fan = cin
+            for s_ in k:
+                fan *= s_
+            sd[name + ".weight"] = (torch.randn(cout, cin, *k, generator=g) * fan ** -0.5).to(torch.bfloat16)
+            sd[name + ".bias"] = (torch.randn(cout, generator=g) * 0.05).to(torch.bfloat16)
+
+        def gamma(name, c, nd):
+            sd[name] = (1.0 + 0.1 * torch.randn(c, *([1] * nd), generator=g)).to(torch.bfloat16)
+
+        def walk(prog, c):
+            """Channel count through the layer list: a residual block changes it where the reference does (the encoder
+            doubles at levels 1 and 2; the decoder halves after each up-sampler and doubles back at level 1)."""
+            for kind, p in prog:
+                if kind == "res":
+                    cout = self._res_out[p]
+                    gamma(p + ".residual.0.gamma", c, 3)
+                    conv(p + ".residual.2", cout, c, 3, 3, 3)
+                    gamma(p + ".residual.3.gamma", cout, 3)
+                    conv(p + ".residual.6", cout, cout, 3, 3, 3)
+                    if c != cout:
+                        conv(p + ".shortcut", cout, c, 1, 1, 1)
+                    c = cout
+                elif kind == "attn":
+                    gamma(p + ".norm.gamma", c, 2)
+                    conv(p + ".to_qkv", 3 * c, c, 1, 1)
+                    conv(p + ".proj", c, c, 1, 1)
+                elif kind in ("down2d", "down3d"):
+                    conv(p + ".resample.1", c, c, 3, 3)
+                    if kind == "down3d":
+                        conv(p + ".time_conv", c, c, 3, 1, 1)
+                else:
+                    if kind == "up3d":
+                        conv(p + ".time_conv", 2 * c, c, 3, 1, 1)
+                    conv(p + ".resample.1", c // 2, c, 3, 3)
+                    c = c // 2
+            return c
+
+        top = self.dim * self._dim_mult[-1]
+        conv("encoder.conv1", self.dim, 3, 3, 3, 3)
+        walk(self._enc, self.dim)
+        gamma("encoder.head.0.gamma", top, 3)
+        conv("encoder.head.2", 2 * self.z_dim, top, 3, 3, 3)
+        conv("conv1", 2 * self.z_dim, 2 * self.z_dim, 1, 1, 1)
+        conv("conv2", self.z_dim, self.z_dim, 1, 1, 1)
+        conv("decoder.conv1", top, self.z_dim, 3, 3, 3)
+        last = walk(self._dec, top)
+        gamma("decoder.head.0.gamma", last, 3)
+        conv("decoder.head.2", 3, last, 3, 3, 3)
+        self.load_vae_state_dict(sd, device=device)
+        return sd
 
     # ----------------------------------------------------------------------------------------------- primitives
     def _conv(self, name: str, grid: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -153,3 +153,38 @@ def test_no_cpu_path():
                           device="cpu")
     with pytest.raises((ValueError, RuntimeError)):
         m.decode_to_pixel(inputs()[1])
+
+
+def test_random_init_has_the_reference_inventory():
+    """init_random_weights (the synthetic stand-in for Wan2.1_VAE.pth) produces exactly the names and shapes the
+    reference's WanVAE_ loads with strict=True (checked against the reference by oracle/make_golden_vae.py)."""
+    from mmpl_b200.vae import WanVAEWrapper
+    sd = WanVAEWrapper().init_random_weights(seed=3, device="cpu")
+    want = V.make_weights(V.VaeConfig(), 0, BF)
+    assert sorted(sd) == sorted(want) == torch.load(GOLDEN)["bf16"]["state_dict_keys"]
+    assert all(sd[k].shape == want[k].shape for k in want)
+
+
+def test_connect_hook_in_the_segment_runner(vae):
+    """SegmentParallelRunner(connect=vae_segment_connect(vae)): the next segment starts from the VAE-connected anchors
+    (Wan_fps_inference_parallel_4gpu_20s.py:191-211), same result as applying the oracle's transform to them."""
+    from mmpl_b200.segment_parallel import AnchorChannel, SegmentParallelRunner, vae_segment_connect
+    seen = {}
+
+    class Pipe:
+        anchor_sink = None
+
+        def inference(self, noise, text_prompts, initial_latent=None, return_latents=True):
+            seen[len(seen)] = initial_latent
+            out = noise.clone()
+            self.anchor_sink(torch.cat([out[:, :1], out[:, [2, 3, 10, 11, 12, 19, 20]]], dim=1))
+            return out, out
+
+    g = torch.Generator().manual_seed(5)
+    noise = [torch.randn(1, 21, 16, 4, 6, generator=g).to(BF) for _ in range(2)]
+    runner = SegmentParallelRunner(Pipe(), AnchorChannel(), anchor_shape=(1, 8, 16, 4, 6), connect=vae_segment_connect(vae))
+    runner.run(lambda seg: noise[seg], ["p"], 2)
+    assert seen[0] is None and seen[1].shape == (1, 2, 16, 4, 6) and seen[1].dtype == BF
+    anchors = torch.cat([noise[0][:, :1], noise[0][:, [2, 3, 10, 11, 12, 19, 20]]], dim=1)
+    want = V.segment_connect_causal(V.make_weights(V.VaeConfig(), 0, BF), V.VaeConfig(), anchors)
+    _close("runner connect", seen[1], want, atol=0.08)

@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
     ap.add_argument("--i2v", action="store_true")
+    ap.add_argument("--vae-connect", action="store_true",
+                    help="run the reference's VAE segment connect (decode anchors, frames 8:13, re-encode) on the hand-off "
+                         "with a seeded random-init VAE (the checkpoint is absent) instead of passing the last two anchors through")
     ap.add_argument("--chains", type=int, default=1,
                     help="independent videos (own prompt / noise) on disjoint rank groups of world/chains ranks each: box throughput")
     ap.add_argument("--cfg-pair", action="store_true",
@@ -103,6 +106,12 @@ def main():
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     runner = SegmentParallelRunner(pipe, channel, anchor_shape=I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE)
+    if a.vae_connect:
+        from mmpl_b200.segment_parallel import vae_segment_connect
+        from mmpl_b200.vae import WanVAEWrapper
+        vae = WanVAEWrapper()
+        vae.init_random_weights(seed=0, device=dev)
+        runner.connect = vae_segment_connect(vae)
 
     def make_noise(seg):
         g = torch.Generator().manual_seed(100 + seg + 1000 * chain)
