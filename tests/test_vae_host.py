@@ -188,3 +188,15 @@ def test_connect_hook_in_the_segment_runner(vae):
     anchors = torch.cat([noise[0][:, :1], noise[0][:, [2, 3, 10, 11, 12, 19, 20]]], dim=1)
     want = V.segment_connect_causal(V.make_weights(V.VaeConfig(), 0, BF), V.VaeConfig(), anchors)
     _close("runner connect", seen[1], want, atol=0.08)
+
+
+def test_i2v_image_encode_and_three_anchor_connect(vae):
+    """MMPL_i2v: the conditioning image is one pixel frame through encode_to_latent
+    (MMPL_i2v/Wan_fps_inference_parallel_4gpu_20s.py:193) and the hand-off payload has 3 anchors (frames 0, 19, 20;
+    lines 212-226: the same transform). Checked against the oracle's streaming restatement."""
+    W, cfg = V.make_weights(V.VaeConfig(), 0, BF), V.VaeConfig()
+    g = torch.Generator().manual_seed(9)
+    image = (torch.rand(1, 3, 1, 32, 48, generator=g) * 2 - 1).to(BF)
+    _close("image encode", vae.encode_to_latent(image), V.encode_to_latent(W, cfg, image), atol=0.06)
+    anchors = torch.randn(1, 3, 16, 4, 6, generator=g).to(BF)
+    _close("i2v connect", vae.segment_connect(anchors), V.segment_connect_causal(W, cfg, anchors), atol=0.08)
