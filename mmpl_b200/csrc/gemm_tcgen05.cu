@@ -44,14 +44,22 @@ struct GemmParams {
   int group_m;         // tile order of the pair kernel: groups of group_m tile rows, row-fastest inside a group
   float* sk_part;      // [pairs][2 CTAs][128 rows][256 columns] fp32 partial accumulators
   uint32_t* sk_flags;  // [pairs][2 CTAs]: 1 = the partial of this CTA's head segment is in sk_part
-  // Tap-GEMM convolution (CONV instantiations of the single-CTA kernel only, see conv3d_cl): the K axis is
-  // taps x channel blocks; k block kb reads channel block kb % conv_kb_per_tap of the A rows shifted by
-  // conv_tap_off[kb / conv_kb_per_tap]; only rows that are interior positions of the padded [.., conv_hp, conv_wp] grid
-  // are stored.
+};
+
+// Tap-GEMM convolution (CONV instantiations of the single-CTA kernel only, see conv3d_cl): the K axis is
+// taps x channel blocks; k block kb reads channel block kb % conv_kb_per_tap of the A rows shifted by
+// conv_tap_off[kb / conv_kb_per_tap]; only rows that are interior positions of the padded [.., conv_hp, conv_wp] grid
+// are stored. A separate (derived) parameter block so that the Linear kernels' parameter layout, and with it their
+// generated code, is exactly what was measured.
+struct ConvGemmParams : GemmParams {
   int conv_kb_per_tap;
   int conv_hp, conv_wp;
   int conv_tap_off[27];
 };
+template <bool CONV>
+struct ParamsOf { using type = GemmParams; };
+template <>
+struct ParamsOf<true> { using type = ConvGemmParams; };
 
 template <int BN>
 struct GemmCfg {
@@ -78,12 +86,12 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // `part` (stream-K owner segments only): `nparts` fp32 partial accumulator rows of this thread's row, `part_stride`
 // floats apart, written by other CTAs; they are added to the TMEM accumulator before the epilogue arithmetic.
 template <int BN, int EPI, bool CONV = false>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int col_base, int c_begin,
+__device__ __forceinline__ void epilogue_tile(const typename ParamsOf<CONV>::type& p, uint32_t taddr, int row, int col_base, int c_begin,
                                               int c_end, const float* part = nullptr, int nparts = 0,
                                               int64_t part_stride = 0) {
   constexpr bool kHasRes = (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES);
   bool row_ok = row < p.M;
-  if (CONV) {
+  if constexpr (CONV) {
     // rows are positions of the zero-haloed grid: the halo stays zero (never written), interior rows are stored
     const int wp = row % p.conv_wp;
     const int hp = (row / p.conv_wp) % p.conv_hp;
@@ -203,7 +211,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+                 const typename ParamsOf<CONV>::type p) {
   using Cfg = GemmCfg<BN>;
   constexpr int ST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -260,7 +268,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx_elect(&full_bar[s], Cfg::kStageBytes);
-        if (CONV) {
+        if constexpr (CONV) {
           // tap-GEMM: the same 128 grid positions shifted by this tap's offset (negative / past-the-end rows and
           // channels beyond Cin are zero-filled by TMA); W is packed [Cout][taps][Cin rounded up to 64]
           const int tap = kb / p.conv_kb_per_tap;
@@ -831,7 +839,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
 // Every grid position (halo included) is one GEMM row; a tap is a row shift of the same A matrix, so the A operand
 // is read in place by TMA: no im2col buffer. The halo rows cost (H+2)(W+2)/(HW) - 1 extra MMA work (0.7 % at 480x832).
 template <int BN, int EPI>
-static int launch_conv(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap* ma, const CUtensorMap* mb, ConvGemmParams p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<BN, EPI, true>;
   static bool attr_set = false;
@@ -866,7 +874,7 @@ int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out,
   const int kb_per_tap = (Cin + kBK - 1) / kBK;
   const int cin64 = kb_per_tap * kBK;
 
-  GemmParams p{};
+  ConvGemmParams p{};
   p.M = static_cast<int>(rows_out);
   p.N = Cout;
   p.K = taps * cin64;
