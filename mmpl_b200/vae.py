@@ -291,6 +291,9 @@ class WanVAEWrapper(torch.nn.Module):
 
     def decode_to_pixel(self, latent: torch.Tensor, use_cache: bool = False) -> torch.Tensor:
         """utils/wan_wrapper.py:91-113: [B, T, z_dim, h, w] -> fp32 [B, T', 3, H, W] clamped to [-1, 1]."""
+        if use_cache:
+            raise NotImplementedError("cached_decode (feature cache kept across calls, vae.py:554-577) is not on the segment-"
+                                      "connect path: every call here decodes its whole frame axis in one pass")
         zs = latent.permute(0, 2, 1, 3, 4)
         out = torch.stack([self._decode_one(u.to(torch.bfloat16)).float().clamp_(-1, 1) for u in zs])
         return out.permute(0, 2, 1, 3, 4)

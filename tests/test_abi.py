@@ -58,6 +58,13 @@ def test_no_cpu_fallback():
     assert rc == -2 and b"sm_100" in lib.mmpl_last_error()
     with pytest.raises(_lib.MmplError):
         _lib.check(rc)
+    # the VAE segment-connect entry points refuse as well (arch check before any pointer is touched)
+    fake = C.c_void_p(0x1000)
+    assert lib.mmpl_conv3d_cl(fake, fake, None, fake, None, 1, 4, 4, 8, 8, 3, 3, 3, None) == -2
+    assert lib.mmpl_vae_norm_act(fake, fake, 16, 8, fake, 1, None) == -2
+    assert lib.mmpl_vae_upsample2x(fake, fake, 1, 4, 4, 8, None) == -2
+    assert lib.mmpl_vae_pick_odd(fake, fake, 1, 4, 4, 8, None) == -2
+    assert lib.mmpl_softmax_rows(fake, 8, fake, 8, 1, 8, 1.0, None) == -2
     from mmpl_b200 import ops
     from mmpl_b200.attention import flash_attention
     from mmpl_b200.causal_model import CausalWanModel
@@ -76,5 +83,5 @@ def test_no_cpu_fallback():
 
 def test_product_does_not_import_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU leg may touch oracle/."""
-    for py in (ROOT / "mmpl_b200").rglob("*.py"):
+    for py in list((ROOT / "mmpl_b200").rglob("*.py")) + list((ROOT / "tools").glob("*.py")):
         assert not re.search(r"^\s*(from|import)\s+oracle\b", py.read_text(), flags=re.M), py
