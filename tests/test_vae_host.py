@@ -200,3 +200,10 @@ def test_i2v_image_encode_and_three_anchor_connect(vae):
     _close("image encode", vae.encode_to_latent(image), V.encode_to_latent(W, cfg, image), atol=0.06)
     anchors = torch.randn(1, 3, 16, 4, 6, generator=g).to(BF)
     _close("i2v connect", vae.segment_connect(anchors), V.segment_connect_causal(W, cfg, anchors), atol=0.08)
+
+
+def test_smoke_vae_leg_runs(vae):
+    """__graft_entry__._smoke_vae_connect (the VAE leg of smoke()) on CPU with the kernel emulations: the smoke code itself."""
+    import __graft_entry__ as ge
+    msg = ge._smoke_vae_connect("cpu")
+    assert msg.startswith("vae connect max_abs=")
