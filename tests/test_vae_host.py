@@ -207,3 +207,23 @@ def test_smoke_vae_leg_runs(vae):
     import __graft_entry__ as ge
     msg = ge._smoke_vae_connect("cpu")
     assert msg.startswith("vae connect max_abs=")
+
+
+@pytest.mark.parametrize("T", [1, 2, 6])
+def test_decode_any_length(vae, T):
+    """The whole-sequence decoder for other frame counts (1 = a single image, 6 -> 21 pixel frames: both temporal
+    up-samplers see several frames) against the oracle's streaming restatement of WanVAE_.decode."""
+    W, cfg = V.make_weights(V.VaeConfig(), 0, BF), V.VaeConfig()
+    lat = torch.randn(1, T, 16, 4, 6, generator=torch.Generator().manual_seed(20 + T)).to(BF)
+    got = vae.decode_to_pixel(lat)
+    assert got.shape == (1, 1 + 4 * (T - 1), 3, 32, 48)
+    _close(f"decode T={T}", got, V.decode_to_pixel(W, cfg, lat), atol=0.06)
+
+
+def test_encode_thirteen_frames(vae):
+    """13 pixel frames -> 4 latents: both temporal down-samplers take more than one stride-2 window."""
+    W, cfg = V.make_weights(V.VaeConfig(), 0, BF), V.VaeConfig()
+    px = (torch.rand(1, 3, 13, 32, 48, generator=torch.Generator().manual_seed(31)) * 2 - 1).to(BF)
+    got = vae.encode_to_latent(px)
+    assert got.shape == (1, 4, 16, 4, 6)
+    _close("encode 13 frames", got, V.encode_to_latent(W, cfg, px), atol=0.06)
