@@ -21,7 +21,10 @@ there is no L2 flush between steps.
            cheapest chunk: 16.2 TFLOP per forward against 28.3 on average over the rollout, so the CPU figure is an
            upper bound for the whole video). `--cpu-sample cfg1` times BASELINE config 0 (30x52 frames) instead.
 N > 1 (torchrun, one rank per GPU): the few-step CausalInferencePipeline path is strictly sequential over chunks, so
-ranks are independent replicas (weak scaling, no data-path collective); see DESIGN.md (e).
+ranks are independent replicas (weak scaling, no data-path collective); see DESIGN.md §6.
+The MMPL segment-parallel mode (BASELINE configs 3-5: Wan2.1-14B, anchors over NCCL, optional CFG-pair lanes and VAE
+segment connect) has the same one-JSON-line driver at tools/run_segment_parallel.py (launched with torchrun the same
+way; measured 1 / 2 / 4 / 8 B200 lines in profiles/).
 """
 from __future__ import annotations
 
