@@ -323,10 +323,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const int row = m_blk * kBM + lane_base + lane;
-      constexpr int kChunks = BN / 32 / 2;  // 32-column chunks per warp
       const int half = (warp - 2) >> 2;
-      epilogue_tile<BN, EPI, CONV>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
-                                   half * kChunks, (half + 1) * kChunks);
+      if constexpr ((BN / 32) % 2 == 0) {
+        constexpr int kChunks = BN / 32 / 2;  // 32-column chunks per warp
+        epilogue_tile<BN, EPI, CONV>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
+                                     half * kChunks, (half + 1) * kChunks);
+      } else {
+        // odd chunk count (BN = 96: three): the left-half warps take the first two, the right-half warps the last
+        constexpr int kChunksLo = (BN / 32 + 1) / 2;
+        epilogue_tile<BN, EPI, CONV>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
+                                     half ? kChunksLo : 0, half ? BN / 32 : kChunksLo);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -892,11 +899,16 @@ int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out,
     for (int dh = 0; dh < KH; ++dh)
       for (int dw = 0; dw < KW; ++dw) p.conv_tap_off[i++] = (dt * Hp + (dh - KH / 2)) * Wp + (dw - KW / 2);
 
-  const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : ((Cout <= 256 || Cout % 256 == 0) ? 256 : 128));
+  int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : ((Cout <= 256 || Cout % 256 == 0) ? 256 : 128));
+  // Opt-in (MMPL_CONV_BN96=1, not yet run on a GPU): 96-wide tiles (UMMA N = 96) for the 96- and 192-channel levels, which
+  // otherwise leave a quarter of a 128- / 256-wide tile's columns empty.
+  static const bool bn96 = getenv("MMPL_CONV_BN96") != nullptr && atoi(getenv("MMPL_CONV_BN96")) != 0;
+  if (bn96 && (Cout == 96 || Cout == 192)) bn = 96;
   const CUtensorMap* ma = get_tensor_map_bf16(in, static_cast<uint64_t>(rows_in), Cin, Cin, kBM);
   const CUtensorMap* mb = get_tensor_map_bf16(w_packed, Cout, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.K), bn);
   if (!ma || !mb) return MMPL_ERR_CUDA;
   const bool res = residual != nullptr;
+  if (bn == 96) return res ? launch_conv<96, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<96, MMPL_EPI_BIAS>(ma, mb, p, stream);
   if (bn == 256) return res ? launch_conv<256, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<256, MMPL_EPI_BIAS>(ma, mb, p, stream);
   if (bn == 128) return res ? launch_conv<128, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<128, MMPL_EPI_BIAS>(ma, mb, p, stream);
   return res ? launch_conv<64, MMPL_EPI_BIAS_RES>(ma, mb, p, stream) : launch_conv<64, MMPL_EPI_BIAS>(ma, mb, p, stream);
