@@ -37,6 +37,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="14B", choices=["14B", "1.3B"])
     ap.add_argument("--segments", type=int, default=4)
+    ap.add_argument("--sweep", default="", help="comma-separated segment counts run back to back on one model build, one "
+                                                 "JSON line each (e.g. 1,2,4,8,12 = 5-60 s videos); overrides --segments")
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
     ap.add_argument("--i2v", action="store_true")
@@ -126,42 +128,49 @@ def main():
             noise=noise, text_prompts=text_prompts, initial_latent=first if initial_latent is None else initial_latent,
             return_latents=return_latents)
 
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    e0.record()
-    model.launch_count(reset=True)
-    outs = runner.run(make_noise, ["synthetic prompt"], a.segments)
-    e1.record()
-    torch.cuda.synchronize()
-    my_ms = e0.elapsed_time(e1)
-    wall = time.perf_counter() - wall0
-    if world > 1:
-        dist.barrier()
-    total_wall = time.perf_counter() - wall0
-    ms = torch.tensor([my_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    finite = all(torch.isfinite(v.float()).all().item() for v in outs.values())
-    info = dict(rank=rank, chain=chain, segments=sorted(outs), ms=my_ms, launches=model.launch_count(), finite=finite,
-                anchor_bytes_sent=channel.bytes_sent, cfg_bytes_exchanged=getattr(pipe, "cfg_bytes_exchanged", 0), log=runner.log,
-                checksum={k: float(v.float().abs().sum()) for k, v in outs.items()})
-    gathered = [info]
-    if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, info)
-    if rank == 0:
-        print(json.dumps({
-            "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
-            "value": a.chains * a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
-            "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.chains} chain(s) x {a.segments} segments x 21 latent frames 60x104, "
-                                   f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
-                       "parallelism": ((f"{a.chains} independent chains, each " if a.chains > 1 else "") + f"segment-parallel x{cworld // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
-                                       ", anchors over NCCL send/recv")},
-            "model_build_s": build_s, "ranks": gathered}))
+    def run_once(nseg):
+        runner.log.clear()
+        channel.bytes_sent = 0
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        e0.record()
+        model.launch_count(reset=True)
+        outs = runner.run(make_noise, ["synthetic prompt"], nseg)
+        e1.record()
+        torch.cuda.synchronize()
+        my_ms = e0.elapsed_time(e1)
+        wall = time.perf_counter() - wall0
+        if world > 1:
+            dist.barrier()
+        total_wall = time.perf_counter() - wall0
+        ms = torch.tensor([my_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        finite = all(torch.isfinite(v.float()).all().item() for v in outs.values())
+        info = dict(rank=rank, chain=chain, segments=sorted(outs), ms=my_ms, launches=model.launch_count(), finite=finite,
+                    anchor_bytes_sent=channel.bytes_sent, cfg_bytes_exchanged=getattr(pipe, "cfg_bytes_exchanged", 0), log=runner.log,
+                    checksum={k: float(v.float().abs().sum()) for k, v in outs.items()})
+        gathered = [info]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, info)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
+                "value": a.chains * nseg * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
+                "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.chains} chain(s) x {nseg} segments x 21 latent frames 60x104, "
+                                       f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
+                           "parallelism": ((f"{a.chains} independent chains, each " if a.chains > 1 else "") + f"segment-parallel x{cworld // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
+                                           ", anchors over NCCL send/recv")},
+                "model_build_s": build_s, "ranks": gathered}))
+
+    # --sweep: several chain lengths against one model build (BASELINE config 5: 5-60 s videos)
+    for nseg in ([int(x) for x in a.sweep.split(',')] if a.sweep else [a.segments]):
+        run_once(nseg)
     if world > 1:
         dist.destroy_process_group()
 
