@@ -106,3 +106,42 @@ def test_service_world4_gloo():
         assert sorted(have) == sorted(want) == list(range(job.num_segments)), job.job_id
         for seg in want:
             assert torch.equal(have[seg], want[seg]), (job.job_id, seg)
+
+
+def _worker_lanes(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        svc = SegmentService(FakeFPSPipeline(), make_noise, ANCHOR, lanes=2)
+        mine = svc.serve([JOBS[2]] if rank == 0 else None)          # one video: 2 slots x 2 lanes, anchors go lane to lane
+        mine2 = svc.serve(LATE if rank == 0 else None)              # two videos: one pair each
+        q.put((rank, {k: {s: v.clone() for s, v in d.items()} for k, d in {**mine, **mine2}.items()}, svc.history))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_service_with_cfg_pair_lanes_world4_gloo():
+    """lanes=2: a segment occupies two consecutive ranks (conditional / unconditional branch) that hold the same latents."""
+    world, port = 4, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_lanes, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    by_rank = {r: o for r, o, _ in got}
+    history = next(h for r, _, h in got if r == 0)
+    assert [(h["job_id"], h["chains"], h["ranks"]) for h in history] == [("c", 1, [0, 1, 2, 3]), ("f", 2, [0, 1]), ("g", 2, [2, 3])]
+    for job in [JOBS[2]] + LATE:
+        want = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(), anchor_shape=ANCHOR).run(
+            lambda seg, job=job: make_noise(job, seg), job.prompts, job.num_segments)
+        for lane in (0, 1):   # both lanes of every pair end with the same latents
+            have = {}
+            for r in range(lane, world, 2):
+                have.update(by_rank[r].get(job.job_id, {}))
+            assert sorted(have) == list(range(job.num_segments)), (job.job_id, lane)
+            for seg in want:
+                assert torch.equal(have[seg], want[seg]), (job.job_id, lane, seg)
