@@ -39,6 +39,10 @@ def main():
     ap.add_argument("--segments", type=int, default=4)
     ap.add_argument("--sweep", default="", help="comma-separated segment counts run back to back on one model build, one "
                                                  "JSON line each (e.g. 1,2,4,8,12 = 5-60 s videos); overrides --segments")
+    ap.add_argument("--videos", type=int, default=0,
+                    help="serve this many queued videos (of --segments segments each, own prompt and noise) through the resident "
+                         "scheduler (mmpl_b200.segment_service): the box is cut into as many chains as videos are waiting")
+    ap.add_argument("--min-slots", type=int, default=1, help="--videos: never cut a chain narrower than this many segment slots")
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
     ap.add_argument("--i2v", action="store_true")
@@ -76,8 +80,12 @@ def main():
     prompt = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(1 + 10 * chain)).to(torch.bfloat16).to(dev)
     negative = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(dev)
 
+    prompt_table = {}  # --videos: one embedding per video's prompt
+
     class Text(torch.nn.Module):
         def forward(self, text_prompts):
+            if text_prompts[0] in prompt_table:
+                return {"prompt_embeds": prompt_table[text_prompts[0]]}
             return {"prompt_embeds": negative if text_prompts[0] == "__negative__" else prompt}
 
     class VAE(torch.nn.Module):
@@ -127,6 +135,47 @@ def main():
         pipe.inference = lambda noise, text_prompts, initial_latent=None, return_latents=True: inference(
             noise=noise, text_prompts=text_prompts, initial_latent=first if initial_latent is None else initial_latent,
             return_latents=return_latents)
+
+    if a.videos:
+        from mmpl_b200.segment_service import SegmentService, VideoJob
+        assert a.chains == 1, "--videos places the chains itself"
+        jobs = [VideoJob(f"video{i}", [f"synthetic prompt {i}"], a.segments, seed=i) for i in range(a.videos)]
+        for j in jobs:
+            prompt_table[j.prompts[0]] = torch.randn(1, 512, 4096, generator=torch.Generator().manual_seed(10 + j.seed)).to(torch.bfloat16).to(dev)
+
+        def job_noise(job, seg):
+            g = torch.Generator().manual_seed(100 + seg + 1000 * job.seed)
+            return torch.randn(1, 21, 16, 60, 104, generator=g).to(torch.bfloat16).to(dev)
+
+        svc = SegmentService(pipe, job_noise, I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE, lanes=lanes, min_slots=a.min_slots,
+                             connect=runner.connect)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = svc.serve(jobs if rank == 0 else None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        finite = all(torch.isfinite(v.float()).all().item() for d in outs.values() for v in d.values())
+        flags = [finite]
+        if world > 1:
+            flags = [None] * world
+            dist.all_gather_object(flags, finite)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
+                "value": a.videos * a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(),
+                "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'}: {a.videos} queued videos x {a.segments} segments x 21 latent "
+                                       f"frames 60x104 through the resident scheduler, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
+                           "parallelism": f"chains chosen per round, {lanes} lane(s) per segment, min {a.min_slots} slot(s) per chain"},
+                "finite": all(flags), "history": svc.history, "model_build_s": build_s}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def run_once(nseg):
         runner.log.clear()
