@@ -160,6 +160,15 @@ int mmpl_patchify(const void* x, int64_t stride_f, int64_t stride_c, void* a, in
 int mmpl_unpatchify_x0(const void* head, int64_t ldh, const void* xt, int64_t xt_stride_f,
                        int64_t xt_stride_c, const double* sigma, void* flow, void* x0, int F, int C, int H,
                        int W, void* stream);
+/* Anchor hand-off between segments: replaces torch.save(latents_chunk{k}.pt) on the producer and the poll / torch.load /
+ * os.remove loop on the consumer (pipeline/casual_fps_inference.py:380-383; Wan_fps_inference_parallel_4gpu_20s.py:183-189)
+ * for a host that owns a raw NCCL communicator: ncclBroadcast of `bytes` bytes at `buf` from rank `root` of `nccl_comm`
+ * (an ncclComm_t), enqueued on `stream` behind the anchor stage's last kernel. In place on every rank. t2v payload
+ * [1,8,16,60,104] bf16 = 1.6 MB, i2v [1,3,16,60,104] = 0.6 MB. NCCL is looked up in the process at run time
+ * (MMPL_ERR_STATE if it is not loaded). The Python host side uses torch.distributed's communicator instead
+ * (mmpl_b200/segment_parallel.py: point-to-point isend / recv on the same stream). */
+int mmpl_anchor_broadcast(void* nccl_comm, void* buf, int64_t bytes, int root, void* stream);
+
 /* FlowMatchScheduler.add_noise (utils/scheduler.py:159-176): bf16((1-sigma_f)*x0 + sigma_f*noise), fp32.
  * sigma: device float [n_frames]; tensors are [n_frames][per_frame] contiguous. */
 int mmpl_add_noise(const void* x0, const void* noise, const float* sigma, void* out, int n_frames,

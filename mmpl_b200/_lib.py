@@ -52,6 +52,7 @@ SIGNATURES = {
     "mmpl_vae_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmpl_vae_pick_odd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmpl_softmax_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]),
+    "mmpl_anchor_broadcast": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "mmpl_flash_attn": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_int_p, c_int_p, c_int_p, c_void_p, c_int64, c_float, c_void_p]),
     "mmpl_gemm_set_streamk": (c_int, [c_int]),

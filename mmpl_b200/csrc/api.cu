@@ -4,6 +4,8 @@
 // segments) is decided by the caller and passed in, so this file contains no cache policy.
 #include <cuda_bf16.h>
 
+#include <dlfcn.h>
+
 #include <cstring>
 #include <string>
 #include <vector>
@@ -137,6 +139,30 @@ int mmpl_vae_pick_odd(const void* in, void* out, int frames, int Hin, int Win, i
 }
 int mmpl_softmax_rows(const void* s, int64_t lds, void* p, int64_t ldp, int rows, int L, float scale, void* stream) {
   COUNTED(softmax_rows(s, lds, p, ldp, rows, L, scale, static_cast<cudaStream_t>(stream)));
+}
+
+// Anchor hand-off for hosts that own a raw NCCL communicator (the Python host side uses torch.distributed's, see
+// mmpl_b200/segment_parallel.py). NCCL is resolved at run time from the process image (torch or the host application has
+// loaded it), falling back to dlopen("libnccl.so.2"): the library keeps loading on a machine without NCCL.
+int mmpl_anchor_broadcast(void* nccl_comm, void* buf, int64_t bytes, int root, void* stream) {
+  MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "anchor_broadcast: requires an sm_100 device");
+  MMPL_CHECK(nccl_comm != nullptr && buf != nullptr && bytes > 0 && root >= 0, MMPL_ERR_ARG, "anchor_broadcast: bad argument");
+  using BcastFn = int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  using ErrFn = const char* (*)(int);
+  static BcastFn bcast = nullptr;
+  static ErrFn errstr = nullptr;
+  if (!bcast) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclBroadcast");
+    void* handle = nullptr;
+    if (!sym && (handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL)) != nullptr) sym = dlsym(handle, "ncclBroadcast");
+    MMPL_CHECK(sym != nullptr, MMPL_ERR_STATE, "anchor_broadcast: NCCL is not loaded in this process (ncclBroadcast not found)");
+    bcast = reinterpret_cast<BcastFn>(sym);
+    errstr = reinterpret_cast<ErrFn>(dlsym(handle ? handle : RTLD_DEFAULT, "ncclGetErrorString"));
+  }
+  constexpr int kNcclUint8 = 1;  // ncclDataType_t: ncclInt8 = 0, ncclUint8 = 1
+  const int rc = bcast(buf, buf, static_cast<size_t>(bytes), kNcclUint8, root, nccl_comm, static_cast<cudaStream_t>(stream));
+  MMPL_CHECK(rc == 0, MMPL_ERR_CUDA, "anchor_broadcast: ncclBroadcast failed: %s", errstr ? errstr(rc) : "unknown");
+  return MMPL_OK;
 }
 
 int mmpl_flash_attn(const void* q, int64_t ldq, int Lq, int H, const void* k0, const void* v0, int64_t ldkv0,

@@ -65,6 +65,7 @@ def test_no_cpu_fallback():
     assert lib.mmpl_vae_upsample2x(fake, fake, 1, 4, 4, 8, None) == -2
     assert lib.mmpl_vae_pick_odd(fake, fake, 1, 4, 4, 8, None) == -2
     assert lib.mmpl_softmax_rows(fake, 8, fake, 8, 1, 8, 1.0, None) == -2
+    assert lib.mmpl_anchor_broadcast(fake, fake, 16, 0, None) == -2
     from mmpl_b200 import ops
     from mmpl_b200.attention import flash_attention
     from mmpl_b200.causal_model import CausalWanModel
