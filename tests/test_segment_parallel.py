@@ -231,3 +231,41 @@ def test_lane_placement():
     assert segments_of_rank(0, 8, 6, lanes=2) == [0, 4] and segments_of_rank(1, 8, 6, lanes=2) == [0, 4]
     assert segments_of_rank(7, 8, 6, lanes=2) == [3] and segments_of_rank(5, 8, 6, lanes=2) == [2]
     assert [producer_of(s, 8, 2, 1) for s in range(5)] == [1, 3, 5, 7, 1]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one checkpoint load per box: rank 0's weights reach every rank over the communicator
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmpl_b200.segment_parallel import broadcast_weights
+        torch.manual_seed(100 + rank)   # every rank starts from different weights
+        m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Linear(32, 8)).to(torch.bfloat16)
+        m.register_buffer("table", torch.randn(5, 3, dtype=torch.float64))
+        n = broadcast_weights(m, src=0, bucket_bytes=600)   # small buckets: several collectives, mixed dtypes
+        q.put((rank, n, {k: v.clone() for k, v in m.state_dict().items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_weights_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((r, (n, sd)) for r, n, sd in [q.get(timeout=120) for _ in range(world)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Linear(32, 8)).to(torch.bfloat16)
+    ref.register_buffer("table", torch.randn(5, 3, dtype=torch.float64))
+    want = ref.state_dict()
+    assert got[0][0] == got[1][0] == sum(v.numel() * v.element_size() for v in want.values())
+    for r in (0, 1):
+        assert sorted(got[r][1]) == sorted(want)
+        for k in want:
+            assert torch.equal(got[r][1][k], want[k]), (r, k)
