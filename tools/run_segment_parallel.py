@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--sampling-steps", type=int, default=50)
     ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0 = the model's own)")
     ap.add_argument("--i2v", action="store_true")
+    ap.add_argument("--broadcast-weights", action="store_true",
+                    help="rank 0's weights are sent to every rank over NCCL (one checkpoint load per box) instead of every rank "
+                         "initialising its own identical replica; the time and bytes go to stderr")
     ap.add_argument("--vae-connect", action="store_true",
                     help="run the reference's VAE segment connect (decode anchors, frames 8:13, re-encode) on the hand-off "
                          "with a seeded random-init VAE (the checkpoint is absent) instead of passing the last two anchors through")
@@ -69,6 +72,14 @@ def main():
     with torch.device(dev):
         model = CausalFPSWanModel(**dims)
     model = model.to(torch.bfloat16).eval().requires_grad_(False)
+    if a.broadcast_weights and world > 1:
+        from mmpl_b200.segment_parallel import broadcast_weights
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
+        nbytes = broadcast_weights(model, src=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"broadcast_weights: {nbytes / 1e9:.1f} GB in {time.perf_counter() - tb:.2f} s", file=sys.stderr)
     gen = WanFPSWrapper(model=model, timestep_shift=5.0)
     build_s = time.perf_counter() - t0
     chain, chain_group, chain_ranks = (0, None, list(range(world)))
