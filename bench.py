@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — denoised latent frames/s of the chunk-wise causal denoising hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny] [--no-chain]
 
 One "step" = one pass of the hot path over one batch of synthetic input: a full CausalInferencePipeline.inference()
 rollout of the workload (cfg2: Wan2.1-T2V-1.3B dims, 21 latent frames at 60x104, 3-frame chunks, 4 denoising steps +
@@ -13,18 +13,28 @@ there is no L2 flush between steps.
 `e2e`    : the same metric through the public API with HOST buffers: pinned-host noise + prompt embeddings copied to
            the device and the denoised latents read back inside the timed region, every step.
 `roofline`: the dominant kernel (tcgen05 self-attention over the KV cache): algorithmic FLOPs / CUDA-event time of its
-           launches during the timed region, against the measured bf16 peak in MEASURED_PEAKS.json.
+           launches during the timed region, against the measured bf16 peak in MEASURED_PEAKS.json; `traffic` comes
+           from the committed ncu capture named in profiles/ncu_traffic.json, and only while the attention kernel's
+           sources still hash to what that capture was taken from.
+`parity` : (N = 1) the first chunk of the same rollout, same weight / noise / prompt seeds and the same re-noising draws,
+           on the GPU path against the CPU arm's output in the same run: max-abs, cosine, finite; plus resident and
+           host-buffer steps giving identical latents.
+`chain`  : the MMPL segment-parallel mode (BASELINE configs 3-5) measured in the same process at every N:
+           Wan2.1-14B dims, CausalFPSWanModel, stages [2,7,6,6], 50 UniPC steps x CFG (fused CFG + UniPC kernel), anchors
+           over NCCL, CFG-pair lanes from 2 GPUs up, VAE segment connect on every hand-off (tools/chain_bench.py). One
+           record per layout (chains x slots x lanes) with frames/s, T_anchor/T_segment, per-rank finish times, anchor
+           bytes, NCCL counts, connect ms and the limiter. The top-level `value` stays the cfg2 replica line so that rounds
+           compare.
 `cpu_baseline` / `--impl reference`: the reference algorithm on the host cores. The reference is pure Python/PyTorch and
-           /root/reference does not exist on the GPU box, so this is the oracle port (oracle/causal_wan_oracle.py) run
-           with native bf16 torch CPU ops (what the reference's CPU path executes), on a bounded sample of the SAME
-           workload: the first of cfg2's seven chunks (3 latent frames at 60x104, 5 forwards, KV length 4680 -- the
-           cheapest chunk: 16.2 TFLOP per forward against 28.3 on average over the rollout, so the CPU figure is an
-           upper bound for the whole video). `--cpu-sample cfg1` times BASELINE config 0 (30x52 frames) instead.
-N > 1 (torchrun, one rank per GPU): the few-step CausalInferencePipeline path is strictly sequential over chunks, so
-ranks are independent replicas (weak scaling, no data-path collective); see DESIGN.md §6.
-The MMPL segment-parallel mode (BASELINE configs 3-5: Wan2.1-14B, anchors over NCCL, optional CFG-pair lanes and VAE
-segment connect) has the same one-JSON-line driver at tools/run_segment_parallel.py (launched with torchrun the same
-way; measured 1 / 2 / 4 / 8 B200 lines in profiles/).
+           /root/reference does not exist on the GPU box, so this is the oracle port (oracle/cpu_port.py: the oracle
+           restatement with native bf16 torch CPU ops, what the reference's CPU path executes; pinned against the
+           reference golden by tests/test_oracle_golden.py). `--impl reference` times the WHOLE cfg2 rollout (same config
+           as the GPU arm; as many steps as fit a time budget, at least one, true count reported). The in-line
+           `cpu_baseline` of the default run is the bounded sample the contract asks for: the first of cfg2's seven
+           chunks (3 latent frames at 60x104, 5 forwards, KV 4680 - the cheapest chunk, so an upper bound).
+N > 1 (torchrun, one rank per GPU): the few-step CausalInferencePipeline path is strictly sequential over chunks, so for
+the top-level line ranks are independent replicas (weak scaling, no data-path collective); the `chain`
+record is where the ranks cooperate.
 """
 from __future__ import annotations
 
@@ -131,8 +141,20 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_run(steps: int, warmup: int, sample: str = "cfg2_chunk0"):
-    """Times the oracle port of the reference pipeline on the host cores (native bf16 torch CPU ops)."""
+RNG_SEED = 1234   # re-noising draws (torch.randn_like in the reference, causal_inference.py:208): a CPU generator on both arms
+
+
+def synthetic_inputs(cfg_dims, frames, lh, lw, noise_seed=0):
+    """Noise [F, C, H, W] and prompt embeddings [text_len, text_dim], bf16: seed 0 / seed 1 on both arms."""
+    text_len, text_dim = cfg_dims.get("text_len", 512), cfg_dims.get("text_dim", 4096)
+    noise = torch.randn(frames, 16, lh, lw, generator=torch.Generator().manual_seed(noise_seed)).to(torch.bfloat16)
+    prompt = torch.randn(text_len, text_dim, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    return noise, prompt
+
+
+def cpu_reference_run(steps: int, warmup: int, sample: str = "cfg2_chunk0", budget_s: float = 0.0):
+    """Times the oracle port of the reference pipeline on the host cores (native bf16 torch CPU ops). With `budget_s`,
+    stops early once another step would not fit (at least one step runs). Returns the last step's latents too."""
     from oracle import causal_wan_oracle as O
     from oracle import cpu_port
     dims, frames, lh, lw = WORKLOADS[sample]
@@ -140,35 +162,41 @@ def cpu_reference_run(steps: int, warmup: int, sample: str = "cfg2_chunk0"):
     torch.set_num_threads(cores)
     cfg = O.WanConfig(**dims)
     w = O.make_weights(cfg, seed=0)
-    g0, g1 = torch.Generator().manual_seed(0), torch.Generator().manual_seed(1)
-    noise = torch.randn(frames, cfg.in_dim, lh, lw, generator=g0).to(torch.bfloat16)
-    prompt = torch.randn(cfg.text_len, cfg.text_dim, generator=g1).to(torch.bfloat16)
-    times = []
+    noise, prompt = synthetic_inputs(dims, frames, lh, lw)
+    times, latents, t_begin = [], None, time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        cpu_port.causal_inference_native(cfg, w, noise, prompt)
+        latents = cpu_port.causal_inference_native(cfg, w, noise, prompt, rng=torch.Generator().manual_seed(RNG_SEED))
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        if budget_s and (time.perf_counter() - t_begin) + dt > budget_s:
+            break
     total = sum(times)
-    return frames * len(times) / total, total / len(times) * 1e3, cores, WORKLOAD_DESC[sample]
+    return dict(value=frames * len(times) / total, ms=total / len(times) * 1e3, cores=cores, sample=WORKLOAD_DESC[sample],
+                steps=len(times), latents=latents)
 
 
 def run_reference(args):
+    """`--impl reference`: the whole workload (same config as the GPU arm) on the host cores. One cfg2 step is ~5 min on 16
+    cores, so there is no warm-up pass and the step count is what fits `--cpu-budget` seconds (at least 1, reported)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # one step is ~40 s on 16 host cores: a warm-up pass only for short runs, so that K = 5 still ends within minutes
-    steps = max(1, args.steps)
-    warmup = max(0, min(args.warmup, 1)) if steps <= 2 else 0
-    value, ms, cores, sample = cpu_reference_run(steps, warmup, args.cpu_sample)
+    sample = args.workload if args.cpu_sample == "same" else args.cpu_sample
+    r = cpu_reference_run(max(1, args.steps), 0, sample, budget_s=args.cpu_budget)
+    same = sample == args.workload
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": 0, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "note": "CPU arm runs a bounded sample, see cpu_baseline.sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD_DESC[args.workload], "same_config": same,
+                   "note": ("whole workload on the host cores; steps = what fits --cpu-budget "
+                            f"({args.cpu_budget:.0f} s), requested {args.steps}") if same else
+                           "CPU arm runs a bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "steps": r["steps"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -203,9 +231,99 @@ def build_pipeline(dims, device, text_len=512, text_dim=4096):
     return pipe, model, holder
 
 
+def ncu_traffic(workload: str):
+    """`roofline.traffic`: DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture that
+    profiles/ncu_traffic.json names, valid only while the kernel's sources still hash to what was captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if workload != "cfg2" or not os.path.exists(path):
+        return None, {"traffic_source": None}
+    with open(path) as f:
+        rec = json.load(f)
+    import hashlib
+    h = hashlib.sha256()
+    for name in rec["sources"]:
+        with open(os.path.join(ROOT, name), "rb") as f:
+            h.update(f.read())
+    current = h.hexdigest()[:16]
+    info = {"traffic_source": rec["capture"], "traffic_launch": rec["launch"], "traffic_algorithmic": rec.get("algorithmic_bytes"),
+            "traffic_kernel_sha": rec["sources_sha"], "traffic_kernel_sha_now": current}
+    return (rec["dram_bytes"] if current == rec["sources_sha"] else None), info
+
+
+def chunk0_parity(pipe, holder, device, cpu_latents):
+    """The first cfg2 chunk on the GPU path with the CPU arm's seeds and re-noising draws, against the CPU arm's latents."""
+    dims, frames, lh, lw = WORKLOADS["cfg2_chunk0"]
+    noise, prompt = synthetic_inputs(dims, frames, lh, lw)
+    holder["prompt"] = prompt[None].to(device)
+    g = torch.Generator().manual_seed(RNG_SEED)
+    orig = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: torch.randn(x.shape, generator=g, dtype=x.dtype).to(x.device)
+    try:
+        lat = pipe.inference(noise=noise[None].to(device), text_prompts=["synthetic"], return_latents=True)[1]
+    finally:
+        torch.randn_like = orig
+    got, ref = lat[0].float().cpu(), cpu_latents.float()
+    return {"what": "cfg2 chunk 0 (3 frames, 5 forwards, 30 blocks): GPU path vs the CPU arm of this run, same seeds and draws",
+            "max_abs": (got - ref).abs().max().item(),
+            "cos": torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item(),
+            "finite": bool(torch.isfinite(got).all())}
+
+
+def run_chain(args, rank, world, device, deadline):
+    """The `chain` record (see the module docstring). Every rank takes part; rank 0 returns the record."""
+    import torch.distributed as dist
+    from tools.chain_bench import ChainBench, limiter_of
+    cb = ChainBench(device, model="14B", layers=args.chain_layers, sampling_steps=args.chain_steps, vae_connect=not args.chain_no_vae)
+    t0 = time.perf_counter()
+    # untimed pass over every rank: communicators, tensor maps, KV caches, VAE workspaces (one 2-step segment per slot)
+    cb.run(1, world // cb.lanes, sampling_steps=2, warm=True)
+    torch.cuda.synchronize()
+    warm_s = time.perf_counter() - t0
+    records, skipped = [], []
+    est_forward_s = 0.30 * cb.dims["num_layers"] / 40   # prior: one 14B forward of ~6 frames on a B200; replaced by measurements
+    for v in cb.variants():
+        segs = 2 if v["slots"] == 1 else (3 * v["slots"] if v["chains"] > 1 else 4)
+        # predicted wall time: segments run back to back on a slot; a chain emits one segment per anchor stage (~0.37 T_seg)
+        steps = args.chain_steps
+        t_seg = est_forward_s * (8 * steps + 8) / v["lanes"]
+        pred = t_seg * (1 + (segs - 1) * max(0.37, 1.0 / v["slots"])) + 5
+        left = deadline - time.perf_counter()
+        if pred > left:
+            steps = max(0, int(steps * (left - 10) / pred))
+        flag = torch.tensor([steps], device=device)
+        if world > 1:
+            dist.broadcast(flag, src=0)   # rank 0's clock decides for everyone
+        steps = int(flag.item())
+        if steps < 8:
+            skipped.append({"layout": f"{v['chains']} chain(s) x {v['slots']} slot(s) x {v['lanes']} lane(s)",
+                            "why": f"{left:.0f} s of the time budget left, {pred:.0f} s needed at {args.chain_steps} steps"})
+            continue
+        rec = cb.run(v["chains"], segs, sampling_steps=steps)
+        t_seg_ms = torch.tensor([rec["t_segment_ms"] if rec else 0.0], device=device)
+        if world > 1:
+            dist.broadcast(t_seg_ms, src=0)
+        if t_seg_ms.item() > 0:
+            est_forward_s = t_seg_ms.item() / 1e3 * v["lanes"] / (8 * steps + 8)
+        if rec is not None:
+            rec["limiter"] = limiter_of(rec)
+            records.append(rec)
+    if rank != 0:
+        return None
+    best = max(records, key=lambda r: r["value"]) if records else None
+    return {
+        "config": {"workload": f"Wan2.1-14B MMPL T2V segment-parallel (BASELINE configs[2]): CausalFPSWanModel, {cb.dims['num_layers']} blocks, "
+                               f"segments of 21 latent frames 60x104, stages [2,7,6,6], {args.chain_steps} UniPC steps x CFG 5.0 "
+                               "(fused CFG + UniPC kernel), anchors over NCCL, VAE segment connect on every hand-off",
+                   "n_gpus": world, "lanes": cb.lanes, "data": "synthetic, random-init weights (model and VAE)"},
+        "value": best["value"] if best else None, "unit": UNIT, "best_layout": best["layout"] if best else None,
+        "variants": records, "skipped": skipped, "model_build_s": round(cb.build_s, 2), "warmup_s": round(warm_s, 2),
+    }
+
+
 def run_ours(args):
     import torch.distributed as dist
     from mmpl_b200 import _lib
+    t_start = time.perf_counter()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,9 +340,9 @@ def run_ours(args):
     mdims = {k: v for k, v in dims.items() if k not in ("text_len", "text_dim")}
     pipe, model, holder = build_pipeline(mdims, device, text_len, text_dim)
 
-    g = torch.Generator().manual_seed(1000 + rank)
-    noise_host = torch.randn(1, frames, 16, lh, lw, generator=g).to(torch.bfloat16).pin_memory()
-    prompt_host = torch.randn(1, text_len, text_dim, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).pin_memory()
+    # the same seeds as the CPU arm on rank 0 (noise 0, prompt 1); other replicas get their own noise
+    noise, prompt = synthetic_inputs(dims, frames, lh, lw, noise_seed=rank)
+    noise_host, prompt_host = noise[None].pin_memory(), prompt[None].pin_memory()
     noise_dev = noise_host.to(device)
     holder["prompt"] = prompt_host.to(device)
     out_host = torch.empty(1, frames, 16, lh, lw, dtype=torch.bfloat16).pin_memory()
@@ -288,6 +406,15 @@ def run_ours(args):
     step_e2e()
     ms_e2e = timed(step_e2e, K)
 
+    # resident and host-buffer steps are the same computation: with the re-noising generator reset they must agree bit for bit
+    torch.manual_seed(RNG_SEED)
+    lat_resident = step_resident().clone()
+    torch.manual_seed(RNG_SEED)
+    step_e2e()
+    torch.cuda.synchronize()
+    e2e_equal = bool(torch.equal(lat_resident.cpu(), out_host))
+    finite = bool(torch.isfinite(lat_resident.float()).all())
+
     # one extra instrumented step: time share per kernel category (not part of any reported throughput)
     _lib.check(lib.mmpl_profile_enable(ctx, 0xF))
     _lib.check(lib.mmpl_profile_read(ctx, ms_arr, work_arr, n_arr, 1))
@@ -309,55 +436,67 @@ def run_ours(args):
                                round(s_work[i] / max(s_ms[i], 1e-9) / (1e9 if i < 8 else 1e6), 1)]
                           for i, nm in enumerate(site_names)}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    out = None
+    if rank == 0:
+        fs = (lh // 2) * (lw // 2)
+        chunks = frames // 3
+        step_flops = sum(forward_flops(mdims, 3 * fs, (c + 1) * 3 * fs, 3, text_len) * 5 for c in range(chunks))
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        value = world * frames * K / (ms_total / 1e3)
+        e2e_value = world * frames * K / (ms_e2e / 1e3)
+        achieved_tf = attn_flops / max(attn_ms, 1e-9) / 1e9
+        traffic, traffic_info = ncu_traffic(args.workload)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "batch": 1, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": ("inputs larger than L2 (no flush): 6 GB KV cache + 2.8 GB weights per step" if args.workload != "cfg2_14b"
+                              else "inputs larger than L2 (no flush): 26.8 GB KV cache + 28 GB weights per step"),
+                       "step_tflop": round(step_flops / 1e12, 1),
+                       "model_tflops_per_gpu": round(step_flops * K / (ms_total / 1e3) / 1e12, 1),
+                       "seeds": {"weights": 0, "noise": "rank", "prompt": 1}},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": noise_host.numel() * 2 + prompt_host.numel() * 2,
+                    "d2h_bytes_per_step": out_host.numel() * 2},
+            "gpu_launches": launches,
+            "roofline": dict({"kernel": "flash_attn_kernel (tcgen05 self-attention over the KV cache)", "bound": "tensor",
+                              "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                              "frac": round(achieved_tf / peak_tf, 4), "traffic": traffic,
+                              "flops_per_launch_avg": round(attn_flops / max(attn_n, 1)), "peak_source": peak_src,
+                              "launches": int(attn_n), "ms_in_timed_region": round(attn_ms, 2),
+                              "share_of_step": round(attn_ms / ms_total, 4)}, **traffic_info),
+            "parity": {"finite": finite, "resident_equals_e2e": e2e_equal},
+            "breakdown": breakdown,
+        }
 
-    fs = (lh // 2) * (lw // 2)
-    chunks = frames // 3
-    step_flops = sum(forward_flops(mdims, 3 * fs, (c + 1) * 3 * fs, 3, text_len) * 5 for c in range(chunks))
-    peak_tf, peak_gbs, peak_src = measured_peaks()
-    value = world * frames * K / (ms_total / 1e3)
-    e2e_value = world * frames * K / (ms_e2e / 1e3)
-    achieved_tf = attn_flops / max(attn_ms, 1e-9) / 1e9
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "batch": 1, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                   "l2": ("inputs larger than L2 (no flush): 6 GB KV cache + 2.8 GB weights per step" if args.workload != "cfg2_14b"
-                          else "inputs larger than L2 (no flush): 26.8 GB KV cache + 28 GB weights per step"),
-                   "step_tflop": round(step_flops / 1e12, 1),
-                   "model_tflops_per_gpu": round(step_flops * K / (ms_total / 1e3) / 1e12, 1)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": noise_host.numel() * 2 + prompt_host.numel() * 2,
-                "d2h_bytes_per_step": out_host.numel() * 2},
-        "gpu_launches": launches,
-        "roofline": {"kernel": "flash_attn_kernel (tcgen05 self-attention over the KV cache)", "bound": "tensor",
-                     "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(achieved_tf / peak_tf, 4),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the L_kv = 32760 launch in
-                     # profiles/r01_ncu_attention_hybrid_vs_cudnn.txt (ncu --set full): 350.5 MB + 24.5 MB; its algorithmic
-                     # K/V + Q + O bytes are 230 MB, the rest is K/V read a second time by the ranged units of the hybrid
-                     # schedule (5 of 12 heads) and their partials (the uniform split it replaced: 231.9 + 63.1 MB and a
-                     # merge kernel with 88 MB more)
-                     "traffic": 375.0e6 if args.workload == "cfg2" else None, "traffic_launch": "L_kv=32760, S=4680, 12 heads",
-                     "flops_per_launch_avg": round(attn_flops / max(attn_n, 1)), "peak_source": peak_src,
-                     "launches": int(attn_n), "ms_in_timed_region": round(attn_ms, 2),
-                     "share_of_step": round(attn_ms / ms_total, 4)},
-        "breakdown": breakdown,
-    }
+    # CPU arm (rank 0 of a 1-GPU run): bounded sample of the same workload + parity of the GPU path against its output
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, sample = cpu_reference_run(steps=1, warmup=0, sample=args.cpu_sample)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms": ms}
-        if args.cpu_sample != "cfg1":
+        sample = "cfg2_chunk0" if args.cpu_sample == "same" else args.cpu_sample
+        r = cpu_reference_run(steps=1, warmup=0, sample=sample)
+        out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"], "ms": r["ms"]}
+        if sample == "cfg2_chunk0" and args.workload == "cfg2":
+            out["parity"].update(chunk0_parity(pipe, holder, device, r["latents"]))
+        if sample != "cfg1":
             # SURVEY.md §8(d) quotes the CPU baseline on BASELINE config 0 (30x52 latent frames: a quarter of the tokens
             # per frame); reported next to the same-workload sample, never used as the headline
-            v1, ms1, _, sample1 = cpu_reference_run(steps=1, warmup=0, sample="cfg1")
-            out["cpu_baseline"]["config0"] = {"value": v1, "unit": UNIT, "sample": sample1, "ms": ms1}
-    print(json.dumps(out))
+            r1 = cpu_reference_run(steps=1, warmup=0, sample="cfg1")
+            out["cpu_baseline"]["config0"] = {"value": r1["value"], "unit": UNIT, "sample": r1["sample"], "ms": r1["ms"]}
+
+    # MMPL segment-parallel chain (configs 3-5), same process, every N
+    if not args.no_chain and args.workload == "cfg2":
+        del pipe, model
+        holder.clear()
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        chain = run_chain(args, rank, world, device, deadline=t_start + args.time_budget)
+        if rank == 0:
+            out["chain"] = chain
+    if rank == 0:
+        out["wall_s"] = round(time.perf_counter() - t_start, 1)
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -370,8 +509,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", default="cfg2_chunk0", choices=["cfg2_chunk0", "cfg1", "tiny"],
-                    help="what the CPU arm (cpu_baseline / --impl reference) times")
+    ap.add_argument("--cpu-sample", default="same", choices=["same", "cfg2_chunk0", "cfg1", "tiny"],
+                    help="what the CPU arm times: `same` = the whole workload for --impl reference and its first chunk for the "
+                         "in-line cpu_baseline")
+    ap.add_argument("--cpu-budget", type=float, default=600.0, help="--impl reference: stop adding steps beyond this many seconds")
+    ap.add_argument("--no-chain", action="store_true", help="skip the MMPL segment-parallel `chain` record")
+    ap.add_argument("--chain-steps", type=int, default=50, help="UniPC steps of the chain record (the reference's 50)")
+    ap.add_argument("--chain-layers", type=int, default=0, help="override the 14B model's 40 blocks (quick checks only)")
+    ap.add_argument("--chain-no-vae", action="store_true", help="pass-through connect instead of the VAE (labelled in the record)")
+    ap.add_argument("--time-budget", type=float, default=780.0,
+                    help="wall seconds the whole run may take: chain layouts that would not fit run with fewer UniPC steps "
+                         "(stated per variant) or are skipped (listed)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MMPL_ABI_VERSION 1
+#define MMPL_ABI_VERSION 2
 
 enum {
   MMPL_OK = 0,
@@ -42,6 +42,9 @@ enum {
 };
 
 int mmpl_abi_version(void);
+/* Identity of the sources this library was built from (mmpl_b200/_build.py: hash of every .cu / header and the
+ * compiler flags). The loader refuses a library whose id differs from the tree it was started from. */
+const char* mmpl_build_id(void);
 const char* mmpl_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------
@@ -173,6 +176,40 @@ int mmpl_anchor_broadcast(void* nccl_comm, void* buf, int64_t bytes, int root, v
  * sigma: device float [n_frames]; tensors are [n_frames][per_frame] contiguous. */
 int mmpl_add_noise(const void* x0, const void* noise, const float* sigma, void* out, int n_frames,
                    int64_t per_frame, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One denoising step of the MMPL hot loop between two backbone forwards:
+ * CFG combine (pipeline/casual_fps_inference.py:366-374) + FlowUniPCMultistepScheduler.step
+ * (wan/utils/fm_solvers_unipc.py:655-739: convert_model_output :318-321, multistep_uni_c_bh_update :486-626,
+ * multistep_uni_p_bh_update :350-484) for solver_order 2 / "bh2" / predict_x0 / flow_prediction, as ONE launch.
+ * The element-wise torch operators of the reference are executed in their order with a bf16 rounding after each, so
+ * the result equals the operator sequence bit for bit. All scalars are host-computed per step:
+ *   flow      = bf16(u + bf16(guidance * bf16(c - u)))                 (flow_uncond == NULL: flow = flow_cond)
+ *   x0        = bf16(x - bf16(sigma * flow))
+ *   corrected = corr_order == 0 ? x :
+ *               bf16( bf16(bf16(corr_a*last) - bf16(corr_b*m1)) - bf16(corr_c * res) ),
+ *               res = bf16(corr_rho1 * bf16(x0 - m1))  [+ bf16(corr_rho0 * D(m2 - m1, corr_rk)) when corr_order == 2]
+ *   next      = bf16( bf16(bf16(pred_a*corrected) - bf16(pred_b*x0)) - bf16(pred_c * 0.5 * D(m1 - x0, pred_rk)) )
+ *               (pred_order == 1: the last term is pred_c * 0)
+ *   D(d, rk)  = true_division ? bf16(bf16(d) / rk) : bf16(rk * bf16(d))
+ * torch evaluates `tensor / cpu_scalar` as a multiplication by the reciprocal on CUDA and as a division on the CPU, and
+ * rounds a CPU scalar to bf16 before `cpu_scalar * tensor` on the CPU only; the host encodes either behaviour in the
+ * coefficients (mmpl_b200/unipc.py) - the default is what the reference computes on a GPU.
+ * m1 / m2 = x0 of the previous / second-previous step (model_outputs[-1], [-2]), last = the corrected sample of the
+ * previous step (last_sample). Outputs may alias the input they replace (next = x, corrected = last, x0_out = m2).
+ * All tensors: n contiguous bf16, 16-byte aligned. */
+typedef struct {
+  float guidance, sigma;
+  int corr_order; /* 0 (first step), 1, 2 */
+  float corr_a, corr_b, corr_c, corr_rk, corr_rho0, corr_rho1;
+  int pred_order; /* 1, 2 */
+  float pred_a, pred_b, pred_c, pred_rk;
+  int true_division;
+} mmpl_unipc_coeffs;
+
+int mmpl_unipc_cfg_step(const void* flow_cond, const void* flow_uncond, const void* x, const void* m1, const void* m2,
+                        const void* last, void* next, void* x0_out, void* corrected_out, int64_t n,
+                        const mmpl_unipc_coeffs* coeffs /* host */, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-forward entry point: CausalWanModel._forward_inference (causal_model.py:763-892) and the

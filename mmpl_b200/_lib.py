@@ -13,6 +13,7 @@ from pathlib import Path
 from . import _build
 
 _LIB = None
+ABI_VERSION = 2  # == MMPL_ABI_VERSION in include/mmpl_b200.h (tests/test_abi.py checks the header)
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
 c_int_p = C.POINTER(C.c_int)
@@ -24,6 +25,16 @@ class ModelConfig(C.Structure):
         ("dim", c_int), ("ffn_dim", c_int), ("num_heads", c_int), ("num_layers", c_int),
         ("freq_dim", c_int), ("text_dim", c_int), ("text_len", c_int), ("in_dim", c_int), ("out_dim", c_int),
         ("eps", c_float), ("max_tokens", c_int),
+    ]
+
+
+class UniPCCoeffs(C.Structure):
+    """mmpl_unipc_coeffs."""
+    _fields_ = [
+        ("guidance", c_float), ("sigma", c_float), ("corr_order", c_int),
+        ("corr_a", c_float), ("corr_b", c_float), ("corr_c", c_float), ("corr_rk", c_float),
+        ("corr_rho0", c_float), ("corr_rho1", c_float), ("pred_order", c_int),
+        ("pred_a", c_float), ("pred_b", c_float), ("pred_c", c_float), ("pred_rk", c_float), ("true_division", c_int),
     ]
 
 
@@ -43,7 +54,10 @@ class ForwardArgs(C.Structure):
 # name -> (restype, argtypes); must list every function declared in include/mmpl_b200.h
 SIGNATURES = {
     "mmpl_abi_version": (c_int, []),
+    "mmpl_build_id": (C.c_char_p, []),
     "mmpl_last_error": (C.c_char_p, []),
+    "mmpl_unipc_cfg_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int64, C.POINTER(UniPCCoeffs), c_void_p]),
     "mmpl_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mmpl_conv3d_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -98,7 +112,9 @@ def lib_path() -> Path:
 
 
 def load(build_if_missing: bool = True):
-    """Load libmmpl_b200.so (building it with nvcc if it is missing or older than its sources)."""
+    """Load libmmpl_b200.so, building it with nvcc first if it does not match the sources in the tree (content hash,
+    mmpl_b200/_build.py). The build is serialised across processes; a failed build raises, and a library whose compiled-in
+    build id or ABI version differs from this tree is refused rather than loaded."""
     global _LIB
     if _LIB is not None:
         return _LIB
@@ -107,21 +123,26 @@ def load(build_if_missing: bool = True):
     if override:
         path, build_if_missing = Path(override), False
     if build_if_missing and _build.is_stale():
-        try:
-            _build.build_library()
-        except Exception:
-            if not path.exists():
-                raise
+        _build.build_library()
     if not path.exists():
         raise ImportError(f"{path} is missing: build it with `python -m mmpl_b200._build` (needs nvcc); "
                           "mmpl_b200 has no CPU fallback")
     lib = C.CDLL(str(path))
     for name, (restype, argtypes) in SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"{path} does not export {name}: the library is older than include/mmpl_b200.h, rebuild it "
+                              "(python -m mmpl_b200._build --force)") from e
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.mmpl_abi_version() != 1:
-        raise ImportError("libmmpl_b200.so ABI version mismatch")
+    if lib.mmpl_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {lib.mmpl_abi_version()}, this binding expects {ABI_VERSION}")
+    if not override:
+        built, want = lib.mmpl_build_id().decode(), _build.source_id()
+        if built != want:
+            raise ImportError(f"{path} was built from other sources (build id {built}, tree {want}): rebuild it with "
+                              "`python -m mmpl_b200._build --force`")
     _LIB = lib
     return lib
 

@@ -127,7 +127,6 @@ class CausalWanModel(nn.Module):
         self._rope_table = None
         self._index_mirror: Dict[int, dict] = {}
         self._param_list = None
-        self._qkv_list = None
         self.last_x0 = None
 
     # ------------------------------------------------------------------------------------------- init
@@ -156,19 +155,31 @@ class CausalWanModel(nn.Module):
             pass
 
     def _param_signature(self):
-        """Cheap per-forward fingerprint of the bound parameters: storage pointers of every parameter (a `.to()` /
-        `.cuda()` moves them) and the version counters of the q/k/v projections (copied into the fused [3D, D] matrix,
-        so an in-place update such as load_state_dict must trigger a re-fuse)."""
+        """Cheap per-forward fingerprint of the bound parameters: storage pointer (a `.to()` / `.cuda()` moves them) and
+        version counter (an in-place update such as load_state_dict or `p.copy_()` bumps it) of every parameter. The q/k/v
+        projections are copied into a fused [3D, D] matrix and non-contiguous parameters into contiguous ones, so any
+        change must re-bind. Contract: the parameter list is re-read after `_apply` (.to / .cuda / .half), `load_state_dict`
+        and `invalidate()`; code that swaps an `nn.Parameter` object or writes through `p.data` calls `invalidate()`."""
         if self._param_list is None:
             self._param_list = list(self.parameters())
-            self._qkv_list = [t for blk in self.blocks for t in
-                              (blk.self_attn.q.weight, blk.self_attn.k.weight, blk.self_attn.v.weight,
-                               blk.self_attn.q.bias, blk.self_attn.k.bias, blk.self_attn.v.bias)]
-        return (tuple(p.data_ptr() for p in self._param_list), tuple(t._version for t in self._qkv_list))
+        return tuple((p.data_ptr(), p._version) for p in self._param_list)
+
+    def invalidate(self):
+        """Forget every host mirror (bound weight pointers, fused q/k/v copies, cache end-index values): the next forward
+        re-reads the parameters and the cache dicts. Call after replacing parameters or editing index tensors behind the
+        model's back."""
+        self._param_list = None
+        self._bound_sig = None
+        self._index_mirror.clear()
 
     def _apply(self, fn, *args, **kwargs):
         self._param_list = None  # parameters may be replaced by .to() / .cuda()
         return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()  # assign=True replaces the Parameter objects; a plain load bumps their versions
+        return out
 
     def _ensure_ctx(self, device: torch.device, tokens: int):
         lib = _lib.load()
@@ -228,18 +239,19 @@ class CausalWanModel(nn.Module):
     def _read_indices(self, kv_cache: Sequence[dict]):
         """Host mirror of global_end_index / local_end_index. The reference reads both with .item() in every
         layer (causal_model.py:210); here the device values are read only when the pipeline has replaced the
-        tensors (cache reset), in one batched copy."""
+        tensors or written them in place (cache reset), in one batched copy."""
         key = id(kv_cache)
         mir = self._index_mirror.get(key)
         if mir is not None and len(mir["g"]) == len(kv_cache) and all(
-                d["global_end_index"] is g and d["local_end_index"] is l
-                for d, g, l in zip(kv_cache, mir["g"], mir["l"])):
+                d["global_end_index"] is g and d["local_end_index"] is l and g._version == vg and l._version == vl
+                for d, g, l, vg, vl in zip(kv_cache, mir["g"], mir["l"], mir["vg"], mir["vl"])):
             return mir
         g = [d["global_end_index"] for d in kv_cache]
         l = [d["local_end_index"] for d in kv_cache]
         vals = torch.stack([t.reshape(-1)[0] for t in g + l]).tolist()
         n = len(kv_cache)
-        mir = {"g": g, "l": l, "gv": [int(v) for v in vals[:n]], "lv": [int(v) for v in vals[n:]]}
+        mir = {"g": g, "l": l, "gv": [int(v) for v in vals[:n]], "lv": [int(v) for v in vals[n:]],
+               "vg": [t._version for t in g], "vl": [t._version for t in l]}
         if len(self._index_mirror) > 8:
             self._index_mirror.clear()
         self._index_mirror[key] = mir
@@ -260,6 +272,8 @@ class CausalWanModel(nn.Module):
             torch._foreach_add_(mir["l"], dl)
         n = len(kv_cache)
         mir["gv"], mir["lv"] = [plan.global_end] * n, [plan.local_end] * n
+        # someone else writing the index tensors in place (e.g. a reset with .zero_()) shows up as a version mismatch
+        mir["vg"], mir["vl"] = [t._version for t in mir["g"]], [t._version for t in mir["l"]]
         return plan
 
     # ---------------------------------------------------------------------------------------- forward
@@ -267,6 +281,13 @@ class CausalWanModel(nn.Module):
         if kwargs.get("kv_cache", None) is None:
             raise NotImplementedError("only the KV-cache inference path (_forward_inference) is implemented; "
                                       "the training path (_forward_train, flex-attention masks) is out of scope")
+        x = args[0] if args else kwargs["x"]
+        dev = x.device if torch.is_tensor(x) else x[0].device
+        if dev.type == "cuda" and dev.index != torch.cuda.current_device():
+            # everything below (context creation, the launches, the stream they go to, the library's per-device caches)
+            # belongs to the device that owns the tensors, whatever device is current in the calling thread
+            with torch.cuda.device(dev):
+                return self._forward_inference(*args, **kwargs)
         return self._forward_inference(*args, **kwargs)
 
     @torch.no_grad()
@@ -304,9 +325,11 @@ class CausalWanModel(nn.Module):
                     if not (torch.is_tensor(tsr) and tsr.shape == (B, self.text_len, H, 128) and tsr.is_cuda
                             and tsr.dtype == torch.bfloat16 and tsr.is_contiguous()):
                         c[n] = torch.empty((B, self.text_len, H, 128), dtype=torch.bfloat16, device=dev)
-        t64 = t.reshape(B, Fn).to(device=dev, dtype=torch.float64).contiguous()
+        # t is [B, F], or [B, 1] broadcast over the frames (the pipelines' t = 0 prefill calls, causal_inference.py:137-169;
+        # the reference broadcasts e0 [B, 1, 6, D] over the frame axis, causal_model.py:297-305)
+        t64 = t.reshape(B, -1).to(device=dev, dtype=torch.float64).expand(B, Fn).contiguous()
         if sigma is not None:
-            sigma = sigma.reshape(B, Fn).to(device=dev, dtype=torch.float64).contiguous()
+            sigma = sigma.reshape(B, -1).to(device=dev, dtype=torch.float64).expand(B, Fn).contiguous()
             x0 = torch.empty((B, Fn, Cc, Hh, Ww), dtype=torch.bfloat16, device=dev)
         flow = torch.empty((B, Fn, self.out_dim, Hh, Ww), dtype=torch.bfloat16, device=dev)
 

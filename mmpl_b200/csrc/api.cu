@@ -114,6 +114,17 @@ static int64_t g_total_launches = 0;
 extern "C" {
 
 int mmpl_abi_version(void) { return MMPL_ABI_VERSION; }
+#ifndef MMPL_BUILD_ID
+#define MMPL_BUILD_ID "unknown"
+#endif
+const char* mmpl_build_id(void) { return MMPL_BUILD_ID; }
+
+int mmpl_unipc_cfg_step(const void* flow_cond, const void* flow_uncond, const void* x, const void* m1, const void* m2,
+                        const void* last, void* next, void* x0_out, void* corrected_out, int64_t n,
+                        const mmpl_unipc_coeffs* coeffs, void* stream) {
+  COUNTED(unipc_cfg_step(flow_cond, flow_uncond, x, m1, m2, last, next, x0_out, corrected_out, n, coeffs,
+                         static_cast<cudaStream_t>(stream)));
+}
 const char* mmpl_last_error(void) { return last_error_buf(); }
 
 int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mmpl_b200.h"
+
 namespace mmpl {
 
 int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
@@ -53,5 +55,10 @@ int unpatchify_x0(const void* head, int64_t ldh, const void* xt, int64_t xt_stri
                   const double* sigma, void* flow, void* x0, int F, int C, int H, int W, cudaStream_t st);
 int add_noise(const void* x0, const void* noise, const float* sigma, void* out, int n_frames, int64_t per_frame,
               cudaStream_t st);
+
+// sampler.cu: CFG combine + flow->x0 + UniPC corrector / predictor in one launch
+int unipc_cfg_step(const void* flow_cond, const void* flow_uncond, const void* sample, const void* m_prev1, const void* m_prev2,
+                   const void* last_sample, void* sample_next, void* x0_out, void* corrected_out, int64_t n,
+                   const mmpl_unipc_coeffs* k, cudaStream_t st);
 
 }  // namespace mmpl

@@ -7,6 +7,7 @@ bf16 tensors whose last dimension is contiguous.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional, Sequence
 
 import torch
@@ -18,6 +19,22 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_RES, EPI_BIAS_GATE_RES = range(
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Runs the wrapped op with the CUDA device of its first tensor argument current, so that the library's launch, the
+    stream handed to it and its per-device caches all belong to the device that owns the pointers (a process may hold
+    models on several GPUs, as the reference's thread-per-GPU drivers do)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -37,6 +54,7 @@ def _ints(v: Sequence[int]):
     return (C.c_int * len(v))(*[int(i) for i in v])
 
 
+@_on_device
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS,
            residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_frame: int = 0,
            out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
@@ -54,6 +72,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+@_on_device
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segments: Optional[Sequence[tuple]] = None,
                k_tail: Optional[torch.Tensor] = None, v_tail: Optional[torch.Tensor] = None,
                softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -82,6 +101,7 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segments: Opti
     return out
 
 
+@_on_device
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, rows_per_frame: int, eps: float = 1e-6,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [S, D]; shift/scale: [frames, D] views sharing a row pitch."""
@@ -96,6 +116,7 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, rows_
     return out
 
 
+@_on_device
 def ln_affine(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     lib = _lib.load()
     _req(x, "x"); _req(weight, "weight"); _req(bias, "bias")
@@ -105,6 +126,7 @@ def ln_affine(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
     return out
 
 
+@_on_device
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, inplace: bool = False) -> torch.Tensor:
     lib = _lib.load()
     _req(x, "x"); _req(weight, "weight")
@@ -114,6 +136,7 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, inplace: b
     return out
 
 
+@_on_device
 def qk_norm_rope_kv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, norm_q_w: torch.Tensor, norm_k_w: torch.Tensor,
                     rope_table: torch.Tensor, k_dst: torch.Tensor, v_dst: torch.Tensor, grid_hw: tuple,
                     frame_pos: Sequence[int], kv_row: Sequence[int], eps: float = 1e-6,
@@ -134,6 +157,7 @@ def qk_norm_rope_kv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, norm_q_w:
     return q_out
 
 
+@_on_device
 def modulation_add(mod: torch.Tensor, src: torch.Tensor, src_fstride: int, src_jstride: int, F: int) -> torch.Tensor:
     """out[f, j, :] = bf16(mod[j, :] + src[f*src_fstride + j*src_jstride + :]); mod: [J, D]."""
     lib = _lib.load()
@@ -145,6 +169,7 @@ def modulation_add(mod: torch.Tensor, src: torch.Tensor, src_fstride: int, src_j
     return out
 
 
+@_on_device
 def sinusoid_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     lib = _lib.load()
     _req(t, "t", torch.float64)
@@ -153,6 +178,7 @@ def sinusoid_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     return out
 
 
+@_on_device
 def skinny_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], silu_in: bool = False,
                   silu_out: bool = False) -> torch.Tensor:
     lib = _lib.load()
@@ -165,6 +191,7 @@ def skinny_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
     return out
 
 
+@_on_device
 def patchify(x: torch.Tensor) -> torch.Tensor:
     """x: [F, C, H, W] (any frame/channel strides, contiguous H*W planes) -> [F*(H/2)*(W/2), C*4]."""
     lib = _lib.load()
@@ -176,6 +203,7 @@ def patchify(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def unpatchify_x0(head: torch.Tensor, shape: tuple, xt: Optional[torch.Tensor] = None,
                   sigma: Optional[torch.Tensor] = None):
     """head: [F*(H/2)*(W/2), 4*C] -> flow [F, C, H, W] (and x0 when xt [F,C,H,W] and sigma float64 [F] are given)."""
@@ -192,6 +220,7 @@ def unpatchify_x0(head: torch.Tensor, shape: tuple, xt: Optional[torch.Tensor] =
     return flow, x0
 
 
+@_on_device
 def add_noise(x0: torch.Tensor, noise: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
     """x0, noise: [N, ...] contiguous bf16; sigma: float32 [N]."""
     lib = _lib.load()
@@ -236,6 +265,7 @@ def from_haloed(g: torch.Tensor, lead: int = 2, channels: Optional[int] = None) 
     return g[lead:, 1:-1, 1:-1, :c].permute(3, 0, 1, 2).contiguous()
 
 
+@_on_device
 def conv3d_causal_cl(grid: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], kernel: Sequence[int],
                      lead: int = 2, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """CausalConv3d.forward (wan/modules/vae.py:16-36), stride 1, on a haloed channels-last grid (see to_haloed).
@@ -267,6 +297,7 @@ def conv3d_causal_cl(grid: torch.Tensor, w_packed: torch.Tensor, bias: Optional[
     return out
 
 
+@_on_device
 def vae_norm_act(grid: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """RMS_norm (+ SiLU) over the channels of every grid position (wan/modules/vae.py:39-55). gamma: any shape with C elements."""
     lib = _lib.load()
@@ -283,6 +314,7 @@ def vae_norm_act(grid: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out
     return out
 
 
+@_on_device
 def vae_upsample2x(grid: torch.Tensor) -> torch.Tensor:
     """Nearest-neighbour 2x up-sampling of every frame of a haloed grid (vae.py:58-64)."""
     lib = _lib.load()
@@ -293,6 +325,7 @@ def vae_upsample2x(grid: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def vae_pick_odd(grid: torch.Tensor) -> torch.Tensor:
     """out interior (i, j) = in interior (2i+1, 2j+1): stride-1 "same" conv -> ZeroPad2d((0,1,0,1)) + stride-2 conv (vae.py:85-88)."""
     lib = _lib.load()
@@ -303,6 +336,7 @@ def vae_pick_odd(grid: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def softmax_rows(s: torch.Tensor, scale: float) -> torch.Tensor:
     """softmax(scale * s) over the last dimension of a 2-D bf16 tensor, fp32 inside."""
     lib = _lib.load()

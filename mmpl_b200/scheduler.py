@@ -1,76 +1,66 @@
-"""FlowMatchScheduler mirror (utils/scheduler.py:106-194): shifted sigma schedule, add_noise, step.
+"""Flow-matching noise schedule of the few-step pipeline: the reference's `FlowMatchScheduler` interface
+(utils/scheduler.py:106-176) reduced to what inference uses — the shifted sigma table, the timestep -> sigma lookup
+and `add_noise` — with `add_noise` on CUDA bf16 latents running the fused `mmpl_add_noise` kernel.
 
-The schedule itself is host-side torch arithmetic identical to the reference (same ops, same dtype, so the
-sigma/timestep tables are bit-identical); `add_noise` on CUDA bf16 latents runs the fused mmpl_add_noise kernel.
+The table is a pure function of (steps, shift, sigma range): `sigma_table()` evaluates the reference's expression with
+the same fp32 torch operators, so `sigmas` / `timesteps` carry the reference's bits. Training-only members of the
+reference class (loss weights, `training_target`, inverse / reversed schedules) are not part of the inference path and
+are rejected rather than carried along.
 """
 from __future__ import annotations
+
+from typing import Dict
 
 import torch
 
 from . import ops
 
 
+def sigma_table(steps: int, shift: float, sigma_min: float, sigma_max: float, extra_one_step: bool,
+                denoising_strength: float = 1.0) -> torch.Tensor:
+    """sigma_k, k = 0..steps-1, descending from sigma_max: a uniform grid warped by s -> shift*s / (1 + (shift-1)*s)
+    (utils/scheduler.py:118-128). `extra_one_step` drops the end point of a (steps+1)-point grid."""
+    top = sigma_min + (sigma_max - sigma_min) * denoising_strength
+    grid = torch.linspace(top, sigma_min, steps + 1)[:-1] if extra_one_step else torch.linspace(top, sigma_min, steps)
+    return shift * grid / (1 + (shift - 1) * grid)
+
+
 class FlowMatchScheduler:
     def __init__(self, num_inference_steps=100, num_train_timesteps=1000, shift=3.0, sigma_max=1.0,
                  sigma_min=0.003 / 1.002, inverse_timesteps=False, extra_one_step=False, reverse_sigmas=False):
-        self.num_train_timesteps = num_train_timesteps
-        self.shift = shift
-        self.sigma_max = sigma_max
-        self.sigma_min = sigma_min
-        self.inverse_timesteps = inverse_timesteps
-        self.extra_one_step = extra_one_step
-        self.reverse_sigmas = reverse_sigmas
+        if inverse_timesteps or reverse_sigmas:
+            raise NotImplementedError("inverse / reversed sigma schedules are not used by the causal inference path")
+        self.num_train_timesteps, self.shift = num_train_timesteps, shift
+        self.sigma_max, self.sigma_min, self.extra_one_step = sigma_max, sigma_min, extra_one_step
+        self._on: Dict[torch.device, tuple] = {}
         self.set_timesteps(num_inference_steps)
 
     def set_timesteps(self, num_inference_steps=100, denoising_strength=1.0, training=False):
-        """utils/scheduler.py:118-142."""
-        sigma_start = self.sigma_min + (self.sigma_max - self.sigma_min) * denoising_strength
-        if self.extra_one_step:
-            self.sigmas = torch.linspace(sigma_start, self.sigma_min, num_inference_steps + 1)[:-1]
-        else:
-            self.sigmas = torch.linspace(sigma_start, self.sigma_min, num_inference_steps)
-        if self.inverse_timesteps:
-            self.sigmas = torch.flip(self.sigmas, dims=[0])
-        self.sigmas = self.shift * self.sigmas / (1 + (self.shift - 1) * self.sigmas)
-        if self.reverse_sigmas:
-            self.sigmas = 1 - self.sigmas
+        """`training=True` is accepted (the wrapper passes it, utils/wan_wrapper.py:141) but only asks the reference for
+        loss weights, which inference never reads."""
+        self.sigmas = sigma_table(num_inference_steps, self.shift, self.sigma_min, self.sigma_max, self.extra_one_step,
+                                  denoising_strength)
         self.timesteps = self.sigmas * self.num_train_timesteps
-        if training:
-            x = self.timesteps
-            y = torch.exp(-2 * ((x - num_inference_steps / 2) / num_inference_steps) ** 2)
-            y_shifted = y - y.min()
-            self.linear_timesteps_weights = y_shifted * (num_inference_steps / y_shifted.sum())
+        self._on.clear()
 
-    def _to(self, device):
-        self.sigmas = self.sigmas.to(device)
-        self.timesteps = self.timesteps.to(device)
+    def tables_on(self, device) -> tuple:
+        """(sigmas, timesteps) resident on `device`, uploaded once."""
+        device = torch.device(device)
+        if self.sigmas.device == device:
+            return self.sigmas, self.timesteps
+        if device not in self._on:
+            self._on[device] = (self.sigmas.to(device), self.timesteps.to(device))
+        return self._on[device]
 
-    def timestep_id(self, timestep):
-        return torch.argmin((self.timesteps.unsqueeze(0) - timestep.unsqueeze(1)).abs(), dim=1)
+    def sigma_at(self, timestep: torch.Tensor) -> torch.Tensor:
+        """sigma of the table entry nearest to each timestep (the reference's argmin lookup, utils/scheduler.py:166-168)."""
+        sigmas, timesteps = self.tables_on(timestep.device)
+        return sigmas[(timesteps[None, :] - timestep.reshape(-1, 1)).abs().argmin(dim=1)]
 
-    def step(self, model_output, timestep, sample, to_final=False):
-        """utils/scheduler.py:144-157."""
-        if timestep.ndim == 2:
-            timestep = timestep.flatten(0, 1)
-        self._to(model_output.device)
-        timestep_id = self.timestep_id(timestep)
-        sigma = self.sigmas[timestep_id].reshape(-1, 1, 1, 1)
-        if to_final or (timestep_id + 1 >= len(self.timesteps)).any():
-            sigma_ = 1 if (self.inverse_timesteps or self.reverse_sigmas) else 0
-        else:
-            sigma_ = self.sigmas[timestep_id + 1].reshape(-1, 1, 1, 1)
-        return sample + model_output * (sigma_ - sigma)
-
-    def add_noise(self, original_samples, noise, timestep):
-        """utils/scheduler.py:159-176: (1 - sigma) * x0 + sigma * noise in fp32, cast to noise.dtype.
-        original_samples / noise: [B*T, C, H, W]; timestep: [B*T]."""
-        if timestep.ndim == 2:
-            timestep = timestep.flatten(0, 1)
-        self._to(noise.device)
-        sigma = self.sigmas[self.timestep_id(timestep)]
-        if noise.is_cuda and noise.dtype == torch.bfloat16 and original_samples.dtype == torch.bfloat16:
-            return ops.add_noise(original_samples.contiguous(), noise.contiguous(), sigma.float().contiguous())
-        raise RuntimeError("mmpl_b200.FlowMatchScheduler.add_noise needs CUDA bfloat16 latents (no CPU fallback)")
-
-    def training_target(self, sample, noise, timestep):
-        return noise - sample
+    def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timestep: torch.Tensor) -> torch.Tensor:
+        """bf16((1 - sigma) * x0 + sigma * noise), fp32 inside (utils/scheduler.py:159-176).
+        original_samples / noise: [N, C, H, W]; timestep: [N] (or [B, T], flattened)."""
+        if not (noise.is_cuda and noise.dtype == torch.bfloat16 and original_samples.dtype == torch.bfloat16):
+            raise RuntimeError("mmpl_b200.FlowMatchScheduler.add_noise needs CUDA bfloat16 latents (no CPU fallback)")
+        sigma = self.sigma_at(timestep.to(noise.device)).float().contiguous()
+        return ops.add_noise(original_samples.contiguous(), noise.contiguous(), sigma)

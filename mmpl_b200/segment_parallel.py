@@ -88,10 +88,11 @@ def broadcast_weights(module: torch.nn.Module, src: int = 0, group: Optional[dis
     return total
 
 
-def default_segment_connect(anchors: torch.Tensor) -> torch.Tensor:
-    """Stand-in for the reference's "segment connect" (decode anchors with the VAE, take pixel frames 8:13, re-encode,
-    keep the first 2 latents; Wan_fps_inference_parallel_4gpu_20s.py:191-205): the VAE is outside the hot path and its
-    weights are absent, so the last two anchor latents (frames 19, 20 of the previous segment) are used directly."""
+def passthrough_connect(anchors: torch.Tensor) -> torch.Tensor:
+    """BENCHMARKING SHORTCUT, not the reference's transform: the last two anchor latents (frames 19, 20 of the previous
+    segment) become the next segment's first two frames as they are. The reference decodes the anchors with the VAE, takes
+    pixel frames 8:13 and re-encodes them (Wan_fps_inference_parallel_4gpu_20s.py:191-205) - that is `vae_segment_connect`.
+    Results produced with this function must say so."""
     return anchors[:, -2:].contiguous()
 
 
@@ -145,14 +146,21 @@ class SegmentParallelRunner:
     """Runs `num_segments` 21-frame segments of one long video across the ranks of the group.
 
     `pipeline` is a CausalFPSInferencePipeline (or anything with `inference(noise, text_prompts, initial_latent=...,
-    return_latents=True)` and a settable `anchor_sink`). `make_noise(segment)` returns that segment's noise tensor."""
+    return_latents=True)` and a settable `anchor_sink`). `connect` turns the anchors received from the previous segment
+    into this segment's `initial_latent`: `vae_segment_connect(vae)` is what the reference does, `passthrough_connect` a
+    labelled shortcut; there is no default, so that no result is produced with the shortcut by accident.
+    `first_initial`: `initial_latent` of segment 0 (the VAE-encoded image of the i2v schedule). `observer(event, segment)`
+    is called at "segment_start", "connect_start", "connect_end" and "segment_end" (timing hooks)."""
 
-    def __init__(self, pipeline, channel: Optional[AnchorChannel] = None, anchor_shape: Sequence[int] = T2V_ANCHOR_SHAPE,
-                 connect: Callable[[torch.Tensor], torch.Tensor] = default_segment_connect):
+    def __init__(self, pipeline, channel: Optional[AnchorChannel], anchor_shape: Sequence[int],
+                 connect: Callable[[torch.Tensor], torch.Tensor], first_initial: Optional[torch.Tensor] = None,
+                 observer: Optional[Callable[[str, int], None]] = None):
         self.pipeline = pipeline
         self.channel = channel or AnchorChannel()
         self.anchor_shape = tuple(anchor_shape)
         self.connect = connect
+        self.first_initial = first_initial
+        self.observer = observer or (lambda event, segment: None)
         self.log: List[tuple] = []
 
     def run(self, make_noise: Callable[[int], torch.Tensor], text_prompts: List[str], num_segments: int) -> Dict[int, torch.Tensor]:
@@ -160,11 +168,14 @@ class SegmentParallelRunner:
         outputs: Dict[int, torch.Tensor] = {}
         for seg in segments_of_rank(ch.rank, ch.world, num_segments, ch.lanes):
             noise = make_noise(seg)
-            initial = None
+            self.observer("segment_start", seg)
+            initial = self.first_initial
             if seg > 0:
                 anchors = ch.recv(seg, (noise.shape[0],) + self.anchor_shape[1:3] + tuple(noise.shape[3:]), noise.dtype, noise.device)
-                initial = self.connect(anchors)
                 self.log.append(("recv", seg, producer_of(seg - 1, ch.world, ch.lanes, ch.lane)))
+                self.observer("connect_start", seg)
+                initial = self.connect(anchors)
+                self.observer("connect_end", seg)
             has_next = seg + 1 < num_segments
 
             def sink(payload, seg=seg, has_next=has_next):
@@ -175,6 +186,7 @@ class SegmentParallelRunner:
             self.pipeline.anchor_sink = sink
             _, latents = self.pipeline.inference(noise=noise, text_prompts=text_prompts, initial_latent=initial,
                                                  return_latents=True)
+            self.observer("segment_end", seg)
             outputs[seg] = latents
         ch.flush()
         return outputs

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import time
 from dataclasses import dataclass, field
-from typing import Callable, Dict, Iterable, List, Optional
+from typing import Callable, Dict, Iterable, Iterator, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -71,12 +71,14 @@ class SegmentService:
     """Resident ranks serving VideoJobs. Every rank of the default process group constructs one and calls `serve`.
 
     `pipeline`: this rank's CausalFPSInferencePipeline (weights resident). `make_noise(job, segment)` returns a segment's
-    noise on this rank's device. `connect`: the anchor transform (vae_segment_connect(vae) or the pass-through default)."""
+    noise on this rank's device. `connect`: the anchor transform - `vae_segment_connect(vae)` is the reference's,
+    `passthrough_connect` a labelled shortcut (required, as for SegmentParallelRunner)."""
 
-    def __init__(self, pipeline, make_noise: Callable[[VideoJob, int], torch.Tensor], anchor_shape, lanes: int = 1,
-                 min_slots: int = 1, connect: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+    def __init__(self, pipeline, make_noise: Callable[[VideoJob, int], torch.Tensor], anchor_shape,
+                 connect: Callable[[torch.Tensor], torch.Tensor], lanes: int = 1, min_slots: int = 1,
+                 first_initial: Optional[torch.Tensor] = None):
         self.pipeline, self.make_noise, self.anchor_shape = pipeline, make_noise, tuple(anchor_shape)
-        self.lanes, self.min_slots, self.connect = lanes, min_slots, connect
+        self.lanes, self.min_slots, self.connect, self.first_initial = lanes, min_slots, connect, first_initial
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if self.world % lanes:
             raise ValueError(f"world size {self.world} is not a multiple of lanes={lanes}")
@@ -85,10 +87,8 @@ class SegmentService:
         chains = 1
         while chains <= self.world // lanes and (self.world // lanes) % chains == 0:
             per = self.world // chains
-            mine = None
-            if chains == 1:
-                mine = None  # the default group
-            else:
+            mine = None  # chains == 1: the default group
+            if chains > 1:
                 for c in range(chains):
                     g = dist.new_group(list(range(c * per, (c + 1) * per)))
                     if self.rank // per == c:
@@ -97,24 +97,52 @@ class SegmentService:
             chains *= 2
         self._runners: Dict[int, SegmentParallelRunner] = {}
         self.history: List[dict] = []   # rank 0: one record per finished job
+        self._seen_ids = set()
 
     def _runner(self, chains: int) -> SegmentParallelRunner:
         if chains not in self._runners:
             channel = AnchorChannel(group=self._groups[chains], lanes=self.lanes)
-            kw = {} if self.connect is None else {"connect": self.connect}
-            self._runners[chains] = SegmentParallelRunner(self.pipeline, channel, anchor_shape=self.anchor_shape, **kw)
+            self._runners[chains] = SegmentParallelRunner(self.pipeline, channel, anchor_shape=self.anchor_shape,
+                                                          connect=self.connect, first_initial=self.first_initial)
         return self._runners[chains]
 
+    def _pull(self, source: Optional[Iterator[VideoJob]], pending: List[VideoJob], want: int) -> Optional[Iterator[VideoJob]]:
+        """Rank 0: tops `pending` up to `want` jobs from the front end's iterator, one `next()` at a time - so a generator
+        that yields requests as they arrive is consulted between rounds, never drained up front. A front end with nothing
+        ready yields `None` (or raises StopIteration when it is closed); neither blocks the box."""
+        while source is not None and len(pending) < want:
+            try:
+                job = next(source)
+            except StopIteration:
+                return None
+            if job is None:   # nothing ready right now
+                break
+            if job.job_id in self._seen_ids:
+                raise ValueError(f"duplicate job id {job.job_id!r}: results and history are keyed by it")
+            self._seen_ids.add(job.job_id)
+            pending.append(job)
+        return source
+
     def serve(self, jobs: Optional[Iterable[VideoJob]] = None) -> Dict[str, Dict[int, torch.Tensor]]:
-        """Runs until the queue is empty. `jobs` is read on rank 0 only (an iterable: a list, or a generator fed by whatever
-        front end owns the requests). Returns {job_id: {segment: latents}} for the segments this rank produced."""
-        pending: List[VideoJob] = list(jobs) if (self.rank == 0 and jobs is not None) else []
+        """Runs until the front end is exhausted and the queue is empty. `jobs` is read on rank 0 only: a list, or a generator
+        fed by whatever front end owns the requests (pulled lazily between rounds, see `_pull`). Returns
+        {job_id: {segment: latents}} for the segments this rank produced."""
+        source = iter(jobs) if (self.rank == 0 and jobs is not None) else None
+        pending: List[VideoJob] = []
         mine: Dict[str, Dict[int, torch.Tensor]] = {}
+        max_chains = max(self._groups)
         while True:
-            box = [plan_round(pending, self.world, self.lanes, self.min_slots) if self.rank == 0 else None]
+            if self.rank == 0:
+                source = self._pull(source, pending, max_chains)
+                if not pending and source is not None:   # the front end is open but idle: ask again instead of quitting
+                    time.sleep(0.001)
+                    source = self._pull(source, pending, max_chains)
+            box = [(plan_round(pending, self.world, self.lanes, self.min_slots), source is not None) if self.rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
-            plan: Optional[RoundPlan] = box[0]
+            plan, front_end_open = box[0]
             if plan is None:
+                if front_end_open:
+                    continue
                 return mine
             per = self.world // plan.chains
             chain = self.rank // per
@@ -130,12 +158,18 @@ class SegmentService:
                 mine.setdefault(job.job_id, {}).update(outs)
                 record = {"job_id": job.job_id, "rank": self.rank, "chain": chain, "chains": plan.chains,
                           "segments": sorted(outs), "seconds": time.perf_counter() - t0}
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, record)
+            # results travel inside the chain's own group to its first rank (a chain that finishes early does not wait for
+            # the others here); the round boundary itself is the plan broadcast above
+            group = self._groups[plan.chains]
+            lead = chain * per
+            parts = [None] * per if self.rank == lead else None
+            dist.gather_object(record, parts, dst=lead, group=group)
+            summary = None
+            if self.rank == lead and job is not None:
+                summary = {"job_id": job.job_id, "chains": plan.chains, "ranks": sorted(r["rank"] for r in parts if r),
+                           "seconds": max(r["seconds"] for r in parts if r), "latent_frames": 21 * job.num_segments}
+            leads = [None] * self.world if self.rank == 0 else None
+            dist.gather_object(summary, leads, dst=0)
             if self.rank == 0:
-                for job in plan.jobs:
-                    parts = [r for r in gathered if r is not None and r["job_id"] == job.job_id]
-                    self.history.append({"job_id": job.job_id, "chains": plan.chains, "ranks": sorted(r["rank"] for r in parts),
-                                         "seconds": max(r["seconds"] for r in parts),
-                                         "latent_frames": 21 * job.num_segments})
+                self.history.extend(x for x in leads if x is not None)
                 pending = pending[len(plan.jobs):]

@@ -43,15 +43,19 @@ class WanDiffusionWrapper(nn.Module):
         self.scheduler = FlowMatchScheduler(shift=timestep_shift, sigma_min=0.0, extra_one_step=True)
         self.scheduler.set_timesteps(1000, training=True)
         self.seq_len = 32760
+        self._tables64 = None
         self.post_init()
 
     def _sigma_of(self, timestep: torch.Tensor) -> torch.Tensor:
-        """float64 sigma_t by nearest-timestep lookup (utils/wan_wrapper.py:186-194)."""
-        sigmas = self.scheduler.sigmas.double().to(timestep.device)
-        timesteps = self.scheduler.timesteps.double().to(timestep.device)
-        flat = timestep.flatten()
-        tid = torch.argmin((timesteps.unsqueeze(0) - flat.unsqueeze(1)).abs(), dim=1)
-        return sigmas[tid].reshape(timestep.shape)
+        """float64 sigma of the schedule entry nearest to each timestep (utils/wan_wrapper.py:186-194); the float64
+        tables live on the device after the first call."""
+        key = (timestep.device, id(self.scheduler.sigmas))
+        if self._tables64 is None or self._tables64[0] != key:
+            self._tables64 = (key, self.scheduler.sigmas.double().to(timestep.device),
+                              self.scheduler.timesteps.double().to(timestep.device))
+        _, sigmas, timesteps = self._tables64
+        nearest = (timesteps[None, :] - timestep.reshape(-1, 1)).abs().argmin(dim=1)
+        return sigmas[nearest].reshape(timestep.shape)
 
     def forward(self, noisy_image_or_video: torch.Tensor, conditional_dict: dict, timestep: torch.Tensor,
                 kv_cache: Optional[List[dict]] = None, crossattn_cache: Optional[List[dict]] = None,

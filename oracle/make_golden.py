@@ -1,5 +1,5 @@
 """ORACLE tooling — generates tests/golden/*.pt by running the UNMODIFIED reference (Tele-AI/MMPL) on CPU
-through oracle/ref_shim.py. Run in the build container only:  python -m oracle.make_golden [tiny] [cfg1] [fps]
+through oracle/ref_shim.py. Run in the build container only:  python -m oracle.make_golden [tiny] [cfg1] [fps] [cfg2]
 
 Every fixture stores what a parity test needs and nothing that can be regenerated from a seed:
   inputs   : seeds / shapes (weights come from oracle.make_weights(cfg, seed), inputs from `synth_inputs`),
@@ -172,6 +172,30 @@ def make_fps():
     torch.save(fix, GOLDEN / "fps_model_tiny.pt")
 
 
+def make_cfg2():
+    """BASELINE.json configs[1] (the benchmarked workload): Wan-1.3B dims, 30 blocks, 21 latent frames at 60x104 in seven
+    3-frame chunks, 4 denoise steps + context pass per chunk = 35 forwards, KV 4680 -> 32760. ~20 minutes on 8 cores.
+    Stored spatially sub-sampled (every 2nd latent row / column) to keep the fixture small: per chunk the x0 of the first
+    (t=1000) and last (t=625) denoising call, and the final latents. The torch.randn_like draws are NOT stored (12.6 MB):
+    they are the CPU generator's stream after torch.manual_seed(rng_seed), regenerated by the test and checked against
+    `eps_sha`."""
+    cfg = O.WAN_1_3B
+    w = O.make_weights(cfg, seed=0)
+    noise, prompt = synth_inputs(cfg, frames=21, lat_h=60, lat_w=104)
+    r = run_reference_causal(cfg, w, noise, prompt, cache_rows=32760)
+    probe = [w["blocks.0.self_attn.q.weight"], w["blocks.29.ffn.2.weight"], w["head.head.weight"], w["patch_embedding.weight"]]
+    sub = lambda t: t[..., ::2, ::2].clone()
+    keep = [i for i in range(len(r["x0"])) if i % 5 in (0, 3)]
+    fix = dict(kind="causal_inference", cfg=cfg.__dict__, weight_seed=0, frames=21, lat_h=60, lat_w=104, cache_rows=32760,
+               steps=(1000, 750, 500, 250), nfpb=3, rng_seed=1234, sub=2,
+               weights_probe_sha=digest(probe), inputs_sha=digest([noise, prompt]), eps_sha=digest(r["eps"]),
+               eps_shapes=[tuple(e.shape) for e in r["eps"]],
+               trace=r["trace"], x0_calls=keep, x0_sub=[sub(r["x0"][i]) for i in keep], latents_sub=sub(r["latents"]),
+               latents_sha=digest([r["latents"]]), ref_seconds=r["seconds"])
+    torch.save(fix, GOLDEN / "causal_cfg2.pt")
+    print("cfg2:", len(r["trace"]), "calls,", f"{r['seconds']:.1f}s", r["trace"][-1])
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     which = sys.argv[1:] or ["tiny", "cfg1"]
@@ -181,3 +205,5 @@ if __name__ == "__main__":
         make_cfg1()
     if "fps" in which:
         make_fps()
+    if "cfg2" in which:
+        make_cfg2()

@@ -23,10 +23,34 @@ def test_library_builds_and_loads_without_gpu():
     path = _build.build_library()
     assert path.exists()
     lib = _lib.load()
-    assert lib.mmpl_abi_version() == 1
+    assert lib.mmpl_abi_version() == _lib.ABI_VERSION
     # no link-time dependency on the driver library: it must load on a box without libcuda.so.1
     out = subprocess.run(["ldd", str(path)], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "libtorch" not in out and "libcudart" not in out
+
+
+def test_abi_version_and_build_id_guard_against_stale_libraries():
+    """The binding's ABI_VERSION is the header's MMPL_ABI_VERSION, the library carries the content hash of the sources it
+    was built from, and the loader compares both (a stale library is rebuilt or refused, never loaded: mmpl_b200/_lib.py)."""
+    assert int(re.search(r"#define MMPL_ABI_VERSION (\d+)", HEADER.read_text()).group(1)) == _lib.ABI_VERSION
+    lib = _lib.load()
+    assert lib.mmpl_build_id().decode() == _build.source_id() == _build.built_id()
+    assert not _build.is_stale()
+
+
+def test_sampler_and_unipc_entry_refuse_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU failure mode")
+    lib = _lib.load()
+    fake = C.c_void_p(0x1000)
+    k = _lib.UniPCCoeffs(5.0, 0.9, 0, 0, 0, 0, 1, 0, 0, 1, 0.5, 0.1, 0.1, 1, 0)
+    assert lib.mmpl_unipc_cfg_step(fake, fake, fake, fake, fake, fake, fake, fake, fake, 64, C.byref(k), None) == -2
+    from mmpl_b200.unipc import FusedUniPC, unipc_table
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedUniPC(unipc_table(3, 5.0, 5.0), torch.zeros(1, 2, 16, 4, 4, dtype=torch.bfloat16))
+    from mmpl_b200.scheduler import FlowMatchScheduler
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlowMatchScheduler(shift=5.0).add_noise(torch.zeros(1, 4, 2, 2, dtype=torch.bfloat16), torch.zeros(1, 4, 2, 2, dtype=torch.bfloat16), torch.zeros(1))
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -12,19 +12,11 @@ import pytest
 import torch
 
 from mmpl_b200.pipeline import CausalDiffusionInferencePipeline, CausalInferencePipeline
-from mmpl_b200.scheduler import FlowMatchScheduler
+from _cpu_ops import cpu_scheduler, eager_unipc_factory
 from oracle.fake_fps_generator import FakeFPSGenerator, digest
 
 GOLDEN = Path(__file__).parent / "golden"
 FIX = torch.load(GOLDEN / "contig_pipelines.pt", weights_only=False)
-
-
-class CpuScheduler(FlowMatchScheduler):
-    """add_noise restated in torch (the product's is a CUDA kernel; utils/scheduler.py:159-176)."""
-
-    def add_noise(self, original_samples, noise, timestep):
-        sigma = self.sigmas[self.timestep_id(timestep.float())].reshape(-1, 1, 1, 1)
-        return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
 
 
 def small_caches(n_blocks=2):
@@ -37,9 +29,7 @@ def small_caches(n_blocks=2):
 @pytest.mark.parametrize("name", sorted(FIX["runs"]))
 def test_mirror_reproduces_the_reference_pipeline(name):
     ref = FIX["runs"][name]
-    sched = CpuScheduler(shift=5.0, sigma_min=0.0, extra_one_step=True)
-    sched.set_timesteps(1000, training=True)
-    gen = FakeFPSGenerator(sched)
+    gen = FakeFPSGenerator(cpu_scheduler())
     text = lambda text_prompts: {"prompt_embeds": torch.full((1, 32, 64), -1.0 if text_prompts[0] == "__negative__" else 1.0,
                                                              dtype=torch.bfloat16)}
     vae = types.SimpleNamespace(decode_to_pixel=lambda latents, use_cache=False: latents)
@@ -59,6 +49,7 @@ def test_mirror_reproduces_the_reference_pipeline(name):
                  independent_first_frame=False, num_frame_per_block=3, model_kwargs={}, sampling_steps=3)
         a.update(ref["over"])
         pipe = CausalDiffusionInferencePipeline(types.SimpleNamespace(**a), torch.device("cpu"), generator=gen, text_encoder=text, vae=vae)
+        pipe.unipc_stepper = eager_unipc_factory(pipe)   # CPU: the fused UniPC kernel's place is taken by the oracle's eager operators
 
         def init_kv(**k):
             pipe.kv_cache_pos, _ = small_caches()

@@ -6,7 +6,7 @@ from pathlib import Path
 import torch
 
 from mmpl_b200.cache_plan import plan_fps
-from mmpl_b200.unipc import FlowUniPCMultistepScheduler
+from oracle.unipc_oracle import FlowUniPCMultistepScheduler
 
 GOLDEN = Path(__file__).parent / "golden"
 

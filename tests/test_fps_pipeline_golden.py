@@ -12,24 +12,14 @@ import pytest
 import torch
 
 from mmpl_b200.pipeline import CausalFPSInferencePipeline
-from mmpl_b200.scheduler import FlowMatchScheduler
+from _cpu_ops import cpu_scheduler, eager_unipc_factory
 from oracle.fake_fps_generator import FakeFPSGenerator, digest
 
 GOLDEN = Path(__file__).parent / "golden"
 
 
-class CpuScheduler(FlowMatchScheduler):
-    """The scheduler mirror with add_noise restated in torch (the product's add_noise is a CUDA kernel; utils/scheduler.py:159-176)."""
-
-    def add_noise(self, original_samples, noise, timestep):
-        sigma = self.sigmas[self.timestep_id(timestep.float())].reshape(-1, 1, 1, 1)
-        return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
-
-
 def build(variant):
-    sched = CpuScheduler(shift=5.0, sigma_min=0.0, extra_one_step=True)
-    sched.set_timesteps(1000, training=True)
-    gen = FakeFPSGenerator(sched)
+    gen = FakeFPSGenerator(cpu_scheduler())
     text = lambda text_prompts: {"prompt_embeds": torch.full((1, 32, 64), -1.0 if text_prompts[0] == "__negative__" else 1.0,
                                                              dtype=torch.bfloat16)}
     vae = types.SimpleNamespace(decode_to_pixel=lambda latents, use_cache=False: latents)
@@ -56,6 +46,7 @@ def test_pipeline_mirror_reproduces_the_reference_pipeline(variant, case):
     sent = []
     pipe = CausalFPSInferencePipeline(args, torch.device("cpu"), generator=gen, text_encoder=text, vae=vae, device_cond="cpu",
                                       device_uncond="cpu", anchor_sink=sent.append)
+    pipe.unipc_stepper = eager_unipc_factory(pipe)   # CPU: the oracle's eager operators stand in for the fused UniPC kernel
     assert torch.equal(pipe.ddmp_timestep, fix["ddmp_timestep"]), "re-noising timestep (constructor randint) differs"
     noise, first, connect = inputs()
     initial = {"plain": None, "extend": connect, "image": first, "connect": connect}[case]

@@ -5,14 +5,8 @@ import types
 import torch
 
 from mmpl_b200.pipeline import CausalInferencePipeline
-from mmpl_b200.scheduler import FlowMatchScheduler
+from _cpu_ops import cpu_scheduler, eager_unipc_factory
 from oracle import causal_wan_oracle as O
-
-
-class FakeScheduler(FlowMatchScheduler):
-    def add_noise(self, original_samples, noise, timestep):  # torch restatement, CPU
-        sigma = self.sigmas[self.timestep_id(timestep.float())].reshape(-1, 1, 1, 1)
-        return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
 
 
 class FakeGenerator(torch.nn.Module):
@@ -20,8 +14,7 @@ class FakeGenerator(torch.nn.Module):
         super().__init__()
         self.model = types.SimpleNamespace(num_layers=3, local_attn_size=-1, num_heads=2, dim=256, text_len=32,
                                            num_frame_per_block=1)
-        self.scheduler = FakeScheduler(shift=5.0, sigma_min=0.0, extra_one_step=True)
-        self.scheduler.set_timesteps(1000, training=True)
+        self.scheduler = cpu_scheduler()
         self.calls = []
 
     def get_scheduler(self):
@@ -99,6 +92,7 @@ def test_cfg_diffusion_pipeline_schedule():
     text = lambda text_prompts: {"tag": "neg" if text_prompts[0] == "neg" else "pos"}  # noqa: E731
     vae = types.SimpleNamespace(decode_to_pixel=lambda latents: latents)
     pipe = CausalDiffusionInferencePipeline(args, torch.device("cpu"), generator=gen, text_encoder=text, vae=vae)
+    pipe.unipc_stepper = eager_unipc_factory(pipe)
     noise = torch.randn(1, 6, 16, 8, 12, generator=torch.Generator().manual_seed(0))
     _, lat = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
     fs = 24

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mmpl_b200.segment_parallel import (AnchorChannel, SegmentParallelRunner, default_segment_connect, make_chain_groups,
+from mmpl_b200.segment_parallel import (AnchorChannel, SegmentParallelRunner, passthrough_connect, make_chain_groups,
                                         producer_of, segments_of_rank)
 
 
@@ -46,7 +46,7 @@ def _worker(rank, world, port, num_segments, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(), anchor_shape=(1, 8, 4, 2, 2))
+        runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(), anchor_shape=(1, 8, 4, 2, 2), connect=passthrough_connect)
         outs = runner.run(lambda seg: torch.full((1, 21, 4, 2, 2), float(seg * 100)), ["p"], num_segments)
         q.put((rank, {k: v[0, :, 0, 0, 0].tolist() for k, v in outs.items()}, runner.log, runner.channel.bytes_sent))
     finally:
@@ -89,7 +89,7 @@ def _chain_worker(rank, world, port, chains, num_segments, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         chain, group, ranks = make_chain_groups(chains)
-        runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(group=group), anchor_shape=(1, 8, 4, 2, 2))
+        runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(group=group), anchor_shape=(1, 8, 4, 2, 2), connect=passthrough_connect)
         outs = runner.run(lambda seg: torch.full((1, 21, 4, 2, 2), float(chain * 1000 + seg * 100)), ["p"], num_segments)
         q.put((rank, chain, ranks, {k: v[0, :, 0, 0, 0].tolist() for k, v in outs.items()}, runner.log))
     finally:
@@ -128,11 +128,11 @@ def test_independent_chains_world4_gloo():
 
 
 def test_single_rank_runs_all_segments_locally():
-    runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(), anchor_shape=(1, 8, 4, 2, 2))
+    runner = SegmentParallelRunner(FakeFPSPipeline(), AnchorChannel(), anchor_shape=(1, 8, 4, 2, 2), connect=passthrough_connect)
     outs = runner.run(lambda seg: torch.zeros(1, 21, 4, 2, 2), ["p"], 3)
     assert sorted(outs) == [0, 1, 2] and outs[2][0, 0, 0, 0, 0].item() == 2.0 and outs[2][0, 5, 0, 0, 0].item() == 1.0
     a = torch.arange(8.).view(1, 8, 1, 1, 1)
-    assert default_segment_connect(a).flatten().tolist() == [6.0, 7.0]
+    assert passthrough_connect(a).flatten().tolist() == [6.0, 7.0]
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -141,20 +141,14 @@ def _fps_pipeline(cfg_group=None):
     import types
 
     from mmpl_b200.pipeline import CausalFPSInferencePipeline
-    from mmpl_b200.scheduler import FlowMatchScheduler
-
-    class CpuScheduler(FlowMatchScheduler):
-        def add_noise(self, original_samples, noise, timestep):  # torch restatement of the CUDA kernel, CPU
-            sigma = self.sigmas[self.timestep_id(timestep.float())].reshape(-1, 1, 1, 1)
-            return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
+    from _cpu_ops import cpu_scheduler, eager_unipc_factory
 
     class FakeGenerator(torch.nn.Module):
         def __init__(self):
             super().__init__()
             self.model = types.SimpleNamespace(num_layers=3, local_attn_size=-1, num_heads=2, dim=256, text_len=32,
                                                num_frame_per_block=1)
-            self.scheduler = CpuScheduler(shift=5.0, sigma_min=0.0, extra_one_step=True)
-            self.scheduler.set_timesteps(1000, training=True)
+            self.scheduler = cpu_scheduler()
 
         def get_scheduler(self):
             return self.scheduler
@@ -176,6 +170,7 @@ def _fps_pipeline(cfg_group=None):
     torch.manual_seed(11)  # constructor randint + the re-noising randn_like draws: same stream on both lanes
     pipe = CausalFPSInferencePipeline(args, torch.device("cpu"), generator=gen, text_encoder=text, vae=vae,
                                       device_cond="cpu", device_uncond="cpu", cfg_group=cfg_group)
+    pipe.unipc_stepper = eager_unipc_factory(pipe)
     return pipe, tags
 
 
@@ -244,7 +239,10 @@ def _bcast_worker(rank, world, port, q):
         m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Linear(32, 8)).to(torch.bfloat16)
         m.register_buffer("table", torch.randn(5, 3, dtype=torch.float64))
         n = broadcast_weights(m, src=0, bucket_bytes=600)   # small buckets: several collectives, mixed dtypes
-        q.put((rank, n, {k: v.clone() for k, v in m.state_dict().items()}))
+        # raw bytes travel through the queue by value (torch tensors would go through shared-memory handles that die with
+        # this process: a race with the parent's q.get)
+        q.put((rank, n, {k: (str(v.dtype), tuple(v.shape), v.contiguous().view(torch.uint8).numpy().tobytes())
+                         for k, v in m.state_dict().items()}))
     finally:
         dist.destroy_process_group()
 
@@ -268,4 +266,6 @@ def test_broadcast_weights_world2_gloo():
     for r in (0, 1):
         assert sorted(got[r][1]) == sorted(want)
         for k in want:
-            assert torch.equal(got[r][1][k], want[k]), (r, k)
+            dtype, shape, raw = got[r][1][k]
+            assert dtype == str(want[k].dtype) and shape == tuple(want[k].shape)
+            assert raw == want[k].contiguous().view(torch.uint8).numpy().tobytes(), (r, k)

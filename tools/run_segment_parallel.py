@@ -29,7 +29,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mmpl_b200.causal_model import CausalFPSWanModel  # noqa: E402
 from mmpl_b200.pipeline import CausalFPSInferencePipeline  # noqa: E402
 from mmpl_b200.segment_parallel import (AnchorChannel, I2V_ANCHOR_SHAPE, SegmentParallelRunner,  # noqa: E402
-                                        T2V_ANCHOR_SHAPE, make_chain_groups)
+                                        T2V_ANCHOR_SHAPE, make_chain_groups, passthrough_connect)
 from mmpl_b200.wan_wrapper import MODEL_CONFIGS, WanFPSWrapper  # noqa: E402
 
 
@@ -126,26 +126,21 @@ def main():
         ops = [dist.P2POp(dist.isend, buf, nxt, chain_group), dist.P2POp(dist.irecv, torch.empty_like(buf), prv, chain_group)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    runner = SegmentParallelRunner(pipe, channel, anchor_shape=I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE)
+    connect, connect_name = passthrough_connect, "pass-through of the last two anchors (benchmarking shortcut, NOT the reference transform)"
     if a.vae_connect:
         from mmpl_b200.segment_parallel import vae_segment_connect
         from mmpl_b200.vae import WanVAEWrapper
         vae = WanVAEWrapper()
         vae.init_random_weights(seed=0, device=dev)
-        runner.connect = vae_segment_connect(vae)
+        connect, connect_name = vae_segment_connect(vae), "VAE decode -> pixel frames 8:13 -> encode (random-init Wan VAE)"
+    # the i2v schedule needs a first frame for segment 0 (VAE-encoded image in the reference)
+    first = torch.randn(1, 1, 16, 60, 104, generator=torch.Generator().manual_seed(7)).to(torch.bfloat16).to(dev) if a.i2v else None
+    runner = SegmentParallelRunner(pipe, channel, anchor_shape=I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE, connect=connect,
+                                   first_initial=first)
 
     def make_noise(seg):
         g = torch.Generator().manual_seed(100 + seg + 1000 * chain)
         return torch.randn(1, 21, 16, 60, 104, generator=g).to(torch.bfloat16).to(dev)
-
-    if a.i2v:  # the i2v schedule needs a first frame for segment 0 (VAE-encoded image in the reference)
-        first = torch.randn(1, 1, 16, 60, 104, generator=torch.Generator().manual_seed(7)).to(torch.bfloat16).to(dev)
-        orig_connect = runner.connect
-        runner.connect = lambda anchors: orig_connect(anchors)
-        inference = pipe.inference
-        pipe.inference = lambda noise, text_prompts, initial_latent=None, return_latents=True: inference(
-            noise=noise, text_prompts=text_prompts, initial_latent=first if initial_latent is None else initial_latent,
-            return_latents=return_latents)
 
     if a.videos:
         from mmpl_b200.segment_service import SegmentService, VideoJob
@@ -158,8 +153,8 @@ def main():
             g = torch.Generator().manual_seed(100 + seg + 1000 * job.seed)
             return torch.randn(1, 21, 16, 60, 104, generator=g).to(torch.bfloat16).to(dev)
 
-        svc = SegmentService(pipe, job_noise, I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE, lanes=lanes, min_slots=a.min_slots,
-                             connect=runner.connect)
+        svc = SegmentService(pipe, job_noise, I2V_ANCHOR_SHAPE if a.i2v else T2V_ANCHOR_SHAPE, connect=connect, lanes=lanes,
+                             min_slots=a.min_slots, first_initial=first)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -183,7 +178,7 @@ def main():
                 "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'}: {a.videos} queued videos x {a.segments} segments x 21 latent "
                                        f"frames 60x104 through the resident scheduler, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
                            "parallelism": f"chains chosen per round, {lanes} lane(s) per segment, min {a.min_slots} slot(s) per chain"},
-                "finite": all(flags), "history": svc.history, "model_build_s": build_s}))
+                "finite": all(flags), "history": svc.history, "connect": connect_name, "model_build_s": build_s}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -226,7 +221,7 @@ def main():
                                        f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
                            "parallelism": ((f"{a.chains} independent chains, each " if a.chains > 1 else "") + f"segment-parallel x{cworld // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
                                            ", anchors over NCCL send/recv")},
-                "model_build_s": build_s, "ranks": gathered}))
+                "connect": connect_name, "model_build_s": build_s, "ranks": gathered}))
 
     # --sweep: several chain lengths against one model build (BASELINE config 5: 5-60 s videos)
     for nseg in ([int(x) for x in a.sweep.split(',')] if a.sweep else [a.segments]):
