@@ -294,6 +294,51 @@ def self_attention(cfg: WanConfig, w: Dict[str, Tensor], pre: str, x: Tensor, gr
     return linear(out.reshape(S, D), w[pre + "o.weight"], w[pre + "o.bias"])
 
 
+def fps_self_attention(cfg: WanConfig, w: Dict[str, Tensor], pre: str, x: Tensor, grid, freqs: Tensor, kv: KVCache,
+                       current_start: Sequence[int], trace: Optional[list] = None) -> Tensor:
+    """CausalWanSelfAttention.forward of the frame-slot (MMPL) model, KV-cache branch (causal_fps_model.py:192-264):
+    `current_start` lists one token offset per frame; frame f's K/V go to slot f (frames 19, 20 to slots 13, 14), the
+    visible set grows by the call's frames and attention reads the visible slots; a call that contains frame 15 (the last
+    stage) writes nothing and attends cat(visible slots, its own K/V). RoPE positions are the frames themselves
+    (causal_fps_rope_apply :27-55: fp32 x times the complex128 table = the same complex128 product as the contiguous model).
+    The reference hard-codes 1560 tokens per frame; here it is the grid's h*w (equal at 60x104)."""
+    S, D = x.shape
+    H, hd = cfg.num_heads, cfg.head_dim
+    fs = grid[1] * grid[2]
+    q = rms_norm(linear(x, w[pre + "q.weight"], w[pre + "q.bias"]), w[pre + "norm_q.weight"], cfg.eps).view(S, H, hd)
+    k = rms_norm(linear(x, w[pre + "k.weight"], w[pre + "k.bias"]), w[pre + "norm_k.weight"], cfg.eps).view(S, H, hd)
+    v = linear(x, w[pre + "v.weight"], w[pre + "v.bias"]).view(S, H, hd)
+    starts = [int(s) for s in current_start]
+    pos = [s // fs for s in starts]
+    rq = rope_apply(q, grid, freqs, pos)
+    rk = rope_apply(k, grid, freqs, pos)
+    slot_row = lambda s: fps_slot_of_frame(s // fs) * fs
+    last_stage = 15 * fs in starts
+    if not last_stage:
+        for i, s in enumerate(starts):
+            kv.k[slot_row(s):slot_row(s) + fs] = rk[i * fs:(i + 1) * fs]
+            kv.v[slot_row(s):slot_row(s) + fs] = v[i * fs:(i + 1) * fs]
+        kv.visible = list(set(kv.visible + starts))
+    else:
+        kv.visible = list(set(kv.visible))
+    rows = torch.cat([torch.arange(slot_row(s), slot_row(s) + fs, device=x.device) for s in kv.visible])
+    if trace is not None:
+        trace.append((sorted(kv.visible), last_stage))
+    if last_stage:
+        out = attention(rq, torch.cat([kv.k[rows], rk]), torch.cat([kv.v[rows], v]))
+    else:
+        out = attention(rq, kv.k[rows], kv.v[rows])
+    return linear(out.reshape(S, D), w[pre + "o.weight"], w[pre + "o.bias"])
+
+
+def fps_model_forward(cfg: WanConfig, w: Dict[str, Tensor], x: Tensor, t: Tensor, context: Tensor, kv_cache: List[KVCache],
+                      cross_cache: List[CrossCache], current_start: Sequence[int], freqs: Optional[Tensor] = None,
+                      trace: Optional[list] = None) -> Tensor:
+    """CausalFPSWanModel._forward_inference (causal_fps_model.py:780-900: the contiguous model's forward with the frame-slot
+    self-attention) for one sample. x [C,F,H,W], t [F], current_start: F token offsets -> flow [C,F,H,W]."""
+    return model_forward(cfg, w, x, t, context, kv_cache, cross_cache, list(current_start), freqs, trace, fps_self_attention)
+
+
 def cross_attention(cfg: WanConfig, w: Dict[str, Tensor], pre: str, x: Tensor, context: Tensor, cc: CrossCache) -> Tensor:
     """WanT2VCrossAttention.forward (model.py:159-194) with the crossattn_cache protocol."""
     S, D = x.shape
@@ -308,13 +353,15 @@ def cross_attention(cfg: WanConfig, w: Dict[str, Tensor], pre: str, x: Tensor, c
 
 
 def block_forward(cfg: WanConfig, w: Dict[str, Tensor], i: int, x: Tensor, e0: Tensor, grid, freqs: Tensor, context: Tensor,
-                  kv: KVCache, cc: CrossCache, current_start: int, trace: Optional[list] = None) -> Tensor:
-    """CausalWanAttentionBlock.forward (causal_model.py:274-326). x [S,D]; e0 [F,6,D]."""
+                  kv: KVCache, cc: CrossCache, current_start, trace: Optional[list] = None, self_attn=None) -> Tensor:
+    """CausalWanAttentionBlock.forward (causal_model.py:274-326). x [S,D]; e0 [F,6,D]. `self_attn` selects the
+    self-attention restatement (default: the contiguous-cache one; `fps_self_attention` for the frame-slot model)."""
+    self_attn = self_attn or self_attention
     b = f"blocks.{i}."
     fs = grid[1] * grid[2]
     e = (w[b + "modulation"].view(1, 6, -1) + e0).unbind(dim=1)  # six [F, D]
-    y = self_attention(cfg, w, b + "self_attn.", modulate(layer_norm(x, cfg.eps), e[0], e[1], fs), grid, freqs, kv,
-                       current_start, trace)
+    y = self_attn(cfg, w, b + "self_attn.", modulate(layer_norm(x, cfg.eps), e[0], e[1], fs), grid, freqs, kv,
+                  current_start, trace)
     x = gate_residual(x, y, e[2], fs)
     x = x + cross_attention(cfg, w, b + "cross_attn.", layer_norm(x, cfg.eps, w[b + "norm3.weight"], w[b + "norm3.bias"]),
                             context, cc)
@@ -340,8 +387,8 @@ def unpatchify(cfg: WanConfig, x: Tensor, grid) -> Tensor:
 
 
 def model_forward(cfg: WanConfig, w: Dict[str, Tensor], x: Tensor, t: Tensor, context: Tensor, kv_cache: List[KVCache],
-                  cross_cache: List[CrossCache], current_start: int, freqs: Optional[Tensor] = None,
-                  trace: Optional[list] = None) -> Tensor:
+                  cross_cache: List[CrossCache], current_start, freqs: Optional[Tensor] = None,
+                  trace: Optional[list] = None, self_attn=None) -> Tensor:
     """CausalWanModel._forward_inference (causal_model.py:763-892) for one sample.
     x [C,F,H,W] latent chunk, t [F] timesteps, context [text_len, text_dim]  ->  flow [C,F,H,W]."""
     if freqs is None:
@@ -357,7 +404,7 @@ def model_forward(cfg: WanConfig, w: Dict[str, Tensor], x: Tensor, t: Tensor, co
     ctx = linear(gelu_tanh(linear(context, w["text_embedding.0.weight"], w["text_embedding.0.bias"])),
                  w["text_embedding.2.weight"], w["text_embedding.2.bias"])
     for i in range(cfg.num_layers):
-        tok = block_forward(cfg, w, i, tok, e0, grid, freqs, ctx, kv_cache[i], cross_cache[i], current_start, trace)
+        tok = block_forward(cfg, w, i, tok, e0, grid, freqs, ctx, kv_cache[i], cross_cache[i], current_start, trace, self_attn)
     # CausalHead (causal_model.py:346-357)
     fs = grid[1] * grid[2]
     eh = (w["head.modulation"].view(1, 2, -1) + e.view(Fn, 1, -1)).unbind(dim=1)

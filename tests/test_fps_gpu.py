@@ -70,15 +70,15 @@ def test_fps_model_matches_reference_golden():
         assert err <= 0.125
 
 
-def test_fps_pipeline_runs_the_macro_from_micro_schedule():
-    """t2v schedule with 3 sampling steps on a 2-block model at 16x24 latents: stage order, forwards per stage
-    (2 per step + 2 context), anchors payload, visibility lists at the end, finite output, determinism."""
-    from mmpl_b200.pipeline import CausalFPSInferencePipeline
-    from mmpl_b200.wan_wrapper import WanFPSWrapper
-    cfg = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
-    gen = WanFPSWrapper(model=_model(cfg, O.make_weights(cfg, 1)), timestep_shift=5.0)
-    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(DEV)
+TINY = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
+# Tolerance of a whole guided rollout (bf16, 3 UniPC steps x CFG 5.0 per stage, 4-5 stages feeding each other through the KV
+# cache): per stage max-abs 0.25 and cosine 0.999 against the oracle-driven trajectory. One forward agrees to max-abs 0.0625 /
+# cosine 0.9999 (tests above); the CFG extrapolation u + 5 (c - u) multiplies a difference between the two branches by up to
+# 9 per step, and later stages attend to the K/V earlier ones wrote.
+STAGE_MAX_ABS, STAGE_MIN_COS = 0.25, 0.999
 
+
+def _text_vae(prompt):
     class Text(torch.nn.Module):
         def forward(self, text_prompts):
             return {"prompt_embeds": prompt if text_prompts[0] != "neg" else -prompt}
@@ -87,72 +87,168 @@ def test_fps_pipeline_runs_the_macro_from_micro_schedule():
         def decode_to_pixel(self, latents, use_cache=False):
             return latents
 
-    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="neg",
-                                 independent_first_frame=False, sampling_steps=3, model_kwargs={})
-    torch.manual_seed(0)
-    anchors = []
-    pipe = CausalFPSInferencePipeline(args, DEV, generator=gen, text_encoder=Text(), vae=VAE(), device_cond=DEV,
-                                      device_uncond=DEV, anchor_sink=anchors.append)
-    calls = []
-    h = gen.register_forward_hook(lambda m, a, kw, out: calls.append(list(kw["current_start"])), with_kwargs=True)
+    return Text(), VAE()
+
+
+def _args(**over):
+    a = dict(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="neg",
+             independent_first_frame=False, sampling_steps=3, model_kwargs={})
+    a.update(over)
+    return types.SimpleNamespace(**a)
+
+
+def _oracle_eager_stepper(pipe):
+    """CFG combine + UniPC step as eager torch operators on the device (tests/_cpu_ops.py): the oracle side of the sampler."""
+    from _cpu_ops import eager_unipc_factory
+    return eager_unipc_factory(pipe)
+
+
+def _compare_stages(name, got, ref):
+    assert len(got) == len(ref) and len(got) > 0
+    for i, (g, r) in enumerate(zip(got, ref)):
+        gf, rf = g.float().cpu(), r.float().cpu()
+        err = (gf - rf).abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(gf.flatten(), rf.flatten(), dim=0).item()
+        print(f"{name} stage {i}: max_abs={err:.4g} cos={cos:.6f} (|ref| mean {rf.abs().mean().item():.3g})")
+        assert torch.isfinite(gf).all()
+        assert err <= STAGE_MAX_ABS and cos >= STAGE_MIN_COS, f"{name} stage {i}: max_abs={err:.4g} cos={cos:.6f}"
+
+
+@pytest.mark.parametrize("variant,initial_frames", [("t2v", 0), ("t2v", 2), ("i2v", 1), ("i2v", 2)])
+def test_fps_pipeline_matches_the_oracle_driven_trajectory(variant, initial_frames):
+    """The MMPL pipeline end to end on the GPU path (CUDA model through mmpl_forward, fused CFG + UniPC kernel, add_noise
+    kernel) against the SAME schedule driven by the oracle (oracle FPS forward + eager sampler operators + oracle add_noise,
+    all plain torch on the device): every stage's latents, the anchor hand-off payload and the final latents within the
+    stated tolerance; call schedule, visible sets and end indices exact. The schedule itself is pinned bit for bit against
+    the reference pipelines on the CPU (tests/test_fps_pipeline_golden.py)."""
+    from mmpl_b200.pipeline import CausalFPSInferencePipeline
+    from mmpl_b200.wan_wrapper import WanFPSWrapper
+    from oracle.oracle_generator import OracleGenerator
+    cfg = TINY
+    w = O.make_weights(cfg, 1)
+    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(DEV)
+    text, vae = _text_vae(prompt)
     noise = torch.randn(1, 21, 16, 16, 24, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).to(DEV)
-    torch.manual_seed(5)
-    _, lat = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
-    h.remove()
+    initial = torch.randn(1, initial_frames, 16, 16, 24, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).to(DEV) \
+        if initial_frames else None
+    args = _args(i2v=variant == "i2v")
     fs = 8 * 12
-    stages = [[0, 1], [2, 3, 10, 11, 12, 19, 20], [4, 5, 6, 7, 8, 9], [13, 14, 15, 16, 17, 18]]
+    runs = {}
+    for side in ("cuda", "oracle"):
+        gen = WanFPSWrapper(model=_model(cfg, w), timestep_shift=5.0) if side == "cuda" else OracleGenerator(cfg, w, fps=True)
+        torch.manual_seed(0)
+        anchors, stages, calls = [], [], []
+        pipe = CausalFPSInferencePipeline(args, DEV, generator=gen, text_encoder=text, vae=vae, device_cond=DEV,
+                                          device_uncond=DEV, anchor_sink=anchors.append)
+        if side == "oracle":
+            pipe.unipc_stepper = _oracle_eager_stepper(pipe)
+        pipe.on_stage = lambda index, rec, latents: stages.append(latents.clone())
+        h = gen.register_forward_hook(lambda m, a, kw, out: calls.append(list(kw["current_start"])), with_kwargs=True)
+        torch.manual_seed(5)
+        _, lat = pipe.inference(noise=noise.clone(), text_prompts=["p"], initial_latent=initial, return_latents=True)
+        h.remove()
+        runs[side] = dict(lat=lat, anchors=anchors, stages=stages, calls=calls,
+                          vis=sorted(pipe.kv_cache_pos[0]["attention_vis_index"]),
+                          ends=(int(pipe.kv_cache_pos[0]["global_end_index"]), int(pipe.kv_cache_neg[-1]["local_end_index"])))
+    a, b = runs["cuda"], runs["oracle"]
+    # exact: schedule, visibility, indices, the frames the anchors are cut from
+    assert a["calls"] == b["calls"] and a["vis"] == b["vis"] == sorted(f * fs for f in list(range(13)) + [19, 20])
+    assert a["ends"] == b["ends"] == (0, 0)
+    stage_frames = [[0, 1], [2, 3, 10, 11, 12, 19, 20], [4, 5, 6, 7, 8, 9], [13, 14, 15, 16, 17, 18]] if variant == "t2v" else \
+        [[0], [1], [2, 3, 10, 11, 12, 19, 20], [4, 5, 6, 7, 8, 9], [13, 14, 15, 16, 17, 18]]
+    prefill = {("t2v", 2): 1, ("i2v", 1): 1, ("i2v", 2): 2}.get((variant, initial_frames), 0)
     expect = []
-    for st in stages:
-        expect += [[f * fs for f in st]] * (2 * 3 + 2)
-    assert calls == expect
-    assert len(anchors) == 1 and anchors[0].shape == (1, 8, 16, 16, 24)
-    assert torch.equal(anchors[0][:, 0], lat[:, 0]) and torch.equal(anchors[0][:, 1:], lat[:, [2, 3, 10, 11, 12, 19, 20]])
-    assert torch.isfinite(lat.float()).all() and lat.float().abs().mean() > 0
-    assert sorted(pipe.kv_cache_pos[0]["attention_vis_index"]) == sorted(f * fs for f in list(range(13)) + [19, 20])
-    # same seeds -> same result (no hidden state between runs; caches are reset in place)
-    torch.manual_seed(5)
-    _, lat2 = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
-    assert torch.equal(lat, lat2)
-    # i2v variant: first frame given, hand-off payload = frames 0, 19, 20
-    args_i = types.SimpleNamespace(**{**vars(args), "i2v": True})
-    anchors_i = []
-    pipe_i = CausalFPSInferencePipeline(args_i, DEV, generator=gen, text_encoder=Text(), vae=VAE(), device_cond=DEV,
-                                        device_uncond=DEV, anchor_sink=anchors_i.append)
-    first = torch.randn(1, 1, 16, 16, 24, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).to(DEV)
-    _, lat_i = pipe_i.inference(noise=noise, text_prompts=["p"], initial_latent=first, return_latents=True)
-    assert torch.equal(lat_i[:, :1], first) and anchors_i[0].shape == (1, 3, 16, 16, 24)
-    assert torch.equal(anchors_i[0], lat_i[:, [0, 19, 20]]) and torch.isfinite(lat_i.float()).all()
+    for i, st in enumerate(stage_frames):
+        n = 2 if i < prefill else 2 * 3 + 2
+        expect += [[f * fs for f in st]] * n
+    assert a["calls"] == expect
+    assert len(a["anchors"]) == 1 and a["anchors"][0].shape == ((1, 8, 16, 16, 24) if variant == "t2v" else (1, 3, 16, 16, 24))
+    if variant == "t2v":
+        assert torch.equal(a["anchors"][0][:, 0], a["lat"][:, 0]) and torch.equal(a["anchors"][0][:, 1:], a["lat"][:, [2, 3, 10, 11, 12, 19, 20]])
+    else:
+        assert torch.equal(a["anchors"][0], a["lat"][:, [0, 19, 20]])
+    if initial is not None:
+        assert torch.equal(a["lat"][:, :initial_frames], initial)
+    # within tolerance: every stage, the hand-off payload, the final latents
+    _compare_stages(f"fps {variant}/{initial_frames}", a["stages"], b["stages"])
+    _compare_stages(f"fps {variant}/{initial_frames} anchors", a["anchors"], b["anchors"])
+    _compare_stages(f"fps {variant}/{initial_frames} final", [a["lat"]], [b["lat"]])
 
 
-def test_cfg_diffusion_pipeline_on_gpu():
-    """CausalDiffusionInferencePipeline mirror end to end on the contiguous-cache model: indices of both caches
-    advance by one chunk per chunk, output finite and reproducible."""
+def test_cfg_diffusion_pipeline_matches_the_oracle_driven_trajectory():
+    """CausalDiffusionInferencePipeline (contiguous cache, UniPC x CFG) on the GPU path against the oracle-driven run of the
+    same schedule: per-chunk latents within tolerance, indices of both caches exact; with a one-chunk prefill
+    (video extension: t = 0 forwards with a [B, 1] timestep) and start_frame_index > 0."""
     from mmpl_b200.causal_model import CausalWanModel
     from mmpl_b200.pipeline import CausalDiffusionInferencePipeline
     from mmpl_b200.wan_wrapper import WanDiffusionWrapper
-    cfg = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
-    m = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
-                       num_heads=cfg.num_heads, num_layers=cfg.num_layers)
-    m.load_state_dict(O.make_weights(cfg, 4))
-    gen = WanDiffusionWrapper(model=m.to(DEV, torch.bfloat16).eval(), timestep_shift=5.0)
+    from oracle.oracle_generator import OracleGenerator
+    cfg = TINY
+    w = O.make_weights(cfg, 4)
     prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(DEV)
-
-    class Text(torch.nn.Module):
-        def forward(self, text_prompts):
-            return {"prompt_embeds": prompt if text_prompts[0] != "neg" else -prompt}
-
-    class VAE(torch.nn.Module):
-        def decode_to_pixel(self, latents, use_cache=False):
-            return latents
-
-    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, guidance_scale=5.0, negative_prompt="neg",
-                                 independent_first_frame=False, num_frame_per_block=3, sampling_steps=3, model_kwargs={})
-    pipe = CausalDiffusionInferencePipeline(args, DEV, generator=gen, text_encoder=Text(), vae=VAE())
+    text, vae = _text_vae(prompt)
     noise = torch.randn(1, 6, 16, 16, 24, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).to(DEV)
-    _, lat = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
+    initial = torch.randn(1, 3, 16, 16, 24, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16).to(DEV)
     fs = 8 * 12
-    for cache in (pipe.kv_cache_pos, pipe.kv_cache_neg):
-        assert int(cache[0]["global_end_index"]) == int(cache[-1]["local_end_index"]) == 6 * fs
-    assert torch.isfinite(lat.float()).all() and lat.float().abs().mean() > 0
-    _, lat2 = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
-    assert torch.equal(lat, lat2)
+    for init, start in ((None, 0), (initial, 2)):
+        runs = {}
+        for side in ("cuda", "oracle"):
+            if side == "cuda":
+                m = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
+                                   num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+                m.load_state_dict(w)
+                gen = WanDiffusionWrapper(model=m.to(DEV, torch.bfloat16).eval(), timestep_shift=5.0)
+            else:
+                gen = OracleGenerator(cfg, w, fps=False)
+            pipe = CausalDiffusionInferencePipeline(_args(num_frame_per_block=3), DEV, generator=gen, text_encoder=text, vae=vae)
+            if side == "oracle":
+                pipe.unipc_stepper = _oracle_eager_stepper(pipe)
+            stages = []
+            pipe.on_stage = lambda index, rec, latents: stages.append(latents.clone())
+            _, lat = pipe.inference(noise=noise, text_prompts=["p"], initial_latent=init, return_latents=True, start_frame_index=start)
+            runs[side] = dict(lat=lat, stages=stages, ends=[(int(c[0]["global_end_index"]), int(c[-1]["local_end_index"]))
+                                                             for c in (pipe.kv_cache_pos, pipe.kv_cache_neg)])
+        total = 6 + (3 if init is not None else 0)
+        # the reference's index recurrence (causal_model.py:203-226) starts local_end at the first call's current_start + S,
+        # so with start_frame_index > 0 both indices end at (start + total) frames
+        assert runs["cuda"]["ends"] == runs["oracle"]["ends"] == [((start + total) * fs, (start + total) * fs)] * 2
+        if init is not None:
+            assert torch.equal(runs["cuda"]["lat"][:, :3], init)
+        _compare_stages(f"cfg-diffusion start={start}", runs["cuda"]["stages"], runs["oracle"]["stages"])
+        _compare_stages(f"cfg-diffusion start={start} final", [runs["cuda"]["lat"]], [runs["oracle"]["lat"]])
+
+
+def test_few_step_pipeline_with_prefill_matches_the_oracle_driven_trajectory():
+    """CausalInferencePipeline with an `initial_latent` (image-to-video / video extension: t = 0 prefill forwards whose
+    timestep tensor is [B, 1], broadcast over the chunk's frames) on the GPU path against the oracle-driven run."""
+    from mmpl_b200.causal_model import CausalWanModel
+    from mmpl_b200.pipeline import CausalInferencePipeline
+    from mmpl_b200.wan_wrapper import WanDiffusionWrapper
+    from oracle.oracle_generator import OracleGenerator
+    cfg = TINY
+    w = O.make_weights(cfg, 6)
+    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(DEV)
+    text, vae = _text_vae(prompt)
+    noise = torch.randn(1, 6, 16, 16, 24, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).to(DEV)
+    initial = torch.randn(1, 3, 16, 16, 24, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16).to(DEV)
+    args = types.SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True, independent_first_frame=False,
+                                 context_noise=0, num_frame_per_block=3, model_kwargs={})
+    runs = {}
+    for side in ("cuda", "oracle"):
+        if side == "cuda":
+            m = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
+                               num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+            m.load_state_dict(w)
+            gen = WanDiffusionWrapper(model=m.to(DEV, torch.bfloat16).eval(), timestep_shift=5.0)
+        else:
+            gen = OracleGenerator(cfg, w, fps=False)
+        pipe = CausalInferencePipeline(args, torch.device(DEV), generator=gen, text_encoder=text, vae=vae)
+        x0s = []
+        pipe.on_call = lambda index, x0: x0s.append(x0.clone())
+        torch.manual_seed(7)
+        _, lat = pipe.inference(noise=noise, text_prompts=["p"], initial_latent=initial, return_latents=True)
+        runs[side] = dict(lat=lat, x0s=x0s, end=int(pipe.kv_cache1[0]["local_end_index"]))
+    assert runs["cuda"]["end"] == runs["oracle"]["end"] == 9 * 8 * 12
+    assert torch.equal(runs["cuda"]["lat"][:, :3], initial) and len(runs["cuda"]["x0s"]) == 8
+    _compare_stages("few-step + prefill x0", runs["cuda"]["x0s"], runs["oracle"]["x0s"])
+    _compare_stages("few-step + prefill final", [runs["cuda"]["lat"]], [runs["oracle"]["lat"]])

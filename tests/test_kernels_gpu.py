@@ -147,6 +147,46 @@ def test_flash_attn_strided_window_and_segments():
     _report("tail", got, ref, 1e-2, 2e-2)
 
 
+def test_flash_attention_call_site_wrapper():
+    """mmpl_b200.attention.flash_attention / attention - the reference call site (wan/modules/attention.py:32-185) - on the
+    GPU: batch of 2, per-sample k_lens and q_lens (rows beyond q_lens come back as zeros, as the reference's packing leaves
+    them), strided q/k/v views (slices of a fused projection and of a larger cache), q_scale / softmax_scale, fp16 inputs
+    returned in q's dtype, and the hot path's plain (q, k, v) call. Each sample against the oracle's attention."""
+    from mmpl_b200.attention import attention, flash_attention
+    B, Lq, Lk, H = 2, 300, 700, 3
+    qkv = _rand(B, Lq, 3 * H * 128, seed=1)
+    q = qkv[..., :H * 128].view(B, Lq, H, 128)                      # row pitch 3*H*128
+    cache = _rand(B, 1000, 2, H, 128, seed=2)
+    k, v = cache[:, 100:100 + Lk, 0], cache[:, 100:100 + Lk, 1]     # strided in the row dimension
+    out = flash_attention(q, k, v)
+    assert out.shape == q.shape and out.dtype == torch.bfloat16
+    for b in range(B):
+        _report(f"call site sample {b}", out[b], O.attention(q[b], k[b], v[b]), 1e-2, 2e-2)
+    q_lens, k_lens = torch.tensor([300, 170]), torch.tensor([700, 333])
+    out = attention(q, k, v, q_lens=q_lens, k_lens=k_lens)
+    for b in range(B):
+        nq, nk = int(q_lens[b]), int(k_lens[b])
+        _report(f"call site lens sample {b}", out[b, :nq], O.attention(q[b, :nq], k[b, :nk], v[b, :nk]), 1e-2, 2e-2)
+        assert (out[b, nq:] == 0).all()
+    # cross-attention's call: k_lens=None over all context rows (model.py:189)
+    ctx_k, ctx_v = _rand(B, 512, H, 128, seed=3), _rand(B, 512, H, 128, seed=4)
+    out = flash_attention(q, ctx_k, ctx_v, k_lens=None)
+    _report("call site cross", out[1], O.attention(q[1], ctx_k[1], ctx_v[1]), 1e-2, 2e-2)
+    # q_scale and softmax_scale
+    out = flash_attention(q, k, v, q_scale=0.5, softmax_scale=0.11)
+    qs = (q * 0.5)
+    ref = O.attention((qs[0].float() * (0.11 * math.sqrt(128))).to(torch.bfloat16), k[0], v[0])
+    _report("call site scales", out[0], ref, 2e-2, 3e-2)
+    # half-precision inputs of the other kind come back in their own dtype
+    out16 = flash_attention(q.to(torch.float16), k.to(torch.float16), v.to(torch.float16))
+    assert out16.dtype == torch.float16
+    _report("call site fp16", out16[0], O.attention(q[0], k[0], v[0]), 1e-2, 2e-2)
+    with pytest.raises(NotImplementedError):
+        flash_attention(q, k, v, causal=True)
+    with pytest.raises(NotImplementedError):
+        flash_attention(q, k, v, window_size=(128, 0))
+
+
 @pytest.mark.parametrize("split", [1, 2, 3, 5])
 def test_flash_attn_forced_kv_split(split):
     """Every unit cut into `split` KV chunks and merged by the combine kernel must equal the unsplit result."""

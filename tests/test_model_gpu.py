@@ -228,3 +228,61 @@ def test_forward_14b_width_matches_oracle():
     ref = O.model_forward(cfg, wd, x[0].permute(1, 0, 2, 3), t[0], prompt[0].to(DEV), okv, ocross, 0)
     _cmp("14B-width flow", flow[0], ref, 0.0625, 0.9999)
     _cmp("14B-width K cache", kv[0]["k"][0], okv[0].k, 0.0625, 0.9999)
+
+
+def test_golden_cfg2_pipeline_full_depth():
+    """BASELINE.json configs[1], the benchmarked workload, at full depth: Wan-1.3B dims, 30 blocks, 21 latent frames at
+    60x104 in seven chunks, 35 forwards, KV 4680 -> 32760, against tests/golden/causal_cfg2.pt recorded from the UNMODIFIED
+    reference on the CPU (oracle/make_golden.py cfg2; 15 minutes there). The golden run's torch.randn_like draws are the CPU
+    generator's stream after manual_seed(rng_seed): regenerated here and checked against the recorded digest, then replayed.
+    Bit-exact: call schedule, timesteps, cache indices. Tolerance per chunk (bf16): x0 of the first and the last denoising
+    call and the final latents max-abs 0.125 / cosine 0.9999, on the stored sub-sampling (every 2nd latent row / column)."""
+    from oracle.make_golden_digest import digest
+    fix = torch.load(GOLDEN / "causal_cfg2.pt", weights_only=False)
+    cfg = O.WanConfig(**fix["cfg"])
+    w = O.make_weights(cfg, fix["weight_seed"])
+    noise, prompt = _synth_inputs(cfg, fix["frames"], fix["lat_h"], fix["lat_w"])
+    assert digest([noise, prompt]) == fix["inputs_sha"], "synthetic inputs differ from the golden run's"
+    g = torch.Generator().manual_seed(fix["rng_seed"])
+    eps = [torch.randn(shape, generator=g, dtype=torch.bfloat16) for shape in fix["eps_shapes"]]
+    assert digest(eps) == fix["eps_sha"], "the CPU generator's stream differs from the golden run's (torch version?)"
+    pipe = build_pipeline(cfg, w, prompt, fix["steps"], fix["nfpb"])
+    trace, x0s, latents = run_with_trace(pipe, noise, eps)
+    assert len(trace) == len(fix["trace"]) == 35
+    for got, ref in zip(trace, fix["trace"]):
+        assert (got["current_start"], got["timestep"], got["global_end"], got["local_end"]) == \\
+            (ref["current_start"], ref["timestep"], ref["global_end"], ref["local_end"]) and got["all_equal"]
+    sub = fix["sub"]
+    for call, ref in zip(fix["x0_calls"], fix["x0_sub"]):
+        _cmp(f"cfg2 chunk {call // 5} call {call} x0 (t={trace[call]['timestep']:.1f}, Lkv={trace[call]['local_end']})",
+             x0s[call][..., ::sub, ::sub], ref, 0.125, 0.9999)
+    _cmp("cfg2 final latents", latents[..., ::sub, ::sub], fix["latents_sub"], 0.125, 0.9999)
+
+
+def test_forward_14b_width_4_blocks_2_chunks_full_resolution():
+    """Wan-14B width (dim 5120, 40 heads, ffn 13824), 4 blocks, two 3-frame chunks at the full 60x104 latent resolution
+    (S = 4680, KV 4680 then 9360): the D = 5120 kernel instantiations, the pair-GEMM tile schedules of the 14B shapes and the
+    40-head attention grid with a second chunk attending to the first one's cache rows, against the oracle on the device.
+    Tolerance: max-abs 0.0625, cosine 0.9999 on the flow; K cache 0.0625 / 0.9999."""
+    from mmpl_b200.causal_model import CausalWanModel
+    cfg = O.WanConfig(dim=5120, ffn_dim=13824, num_heads=40, num_layers=4)
+    w = O.make_weights(cfg, seed=11)
+    noise, prompt = _synth_inputs(cfg, 6, 60, 104)
+    model = CausalWanModel(dim=cfg.dim, ffn_dim=cfg.ffn_dim, num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+    model.load_state_dict(w)
+    model = model.to(DEV, torch.bfloat16).eval()
+    fs, rows = 1560, 6 * 1560
+    kv = [{"k": torch.zeros(1, rows, 40, 128, dtype=torch.bfloat16, device=DEV), "v": torch.zeros(1, rows, 40, 128, dtype=torch.bfloat16, device=DEV),
+           "global_end_index": torch.tensor([0], device=DEV), "local_end_index": torch.tensor([0], device=DEV)} for _ in range(4)]
+    cross = [{"k": None, "v": None, "is_init": False} for _ in range(4)]
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    okv, ocross = O.new_caches(cfg, rows, device=DEV)
+    for chunk, t_val in ((0, 937.5), (1, 625.0)):
+        x = noise[:, chunk * 3:(chunk + 1) * 3].to(DEV)
+        t = torch.full((1, 3), t_val, device=DEV)
+        flow = model(x.permute(0, 2, 1, 3, 4), t=t, context=prompt.to(DEV), seq_len=32760, kv_cache=kv, crossattn_cache=cross,
+                     current_start=chunk * 3 * fs)
+        ref = O.model_forward(cfg, wd, x[0].permute(1, 0, 2, 3), t[0], prompt[0].to(DEV), okv, ocross, chunk * 3 * fs)
+        _cmp(f"14B-width 4 blocks chunk {chunk} flow", flow[0], ref, 0.0625, 0.9999)
+        assert int(kv[0]["local_end_index"].item()) == okv[0].local_end_index == (chunk + 1) * 3 * fs
+    _cmp("14B-width K cache, last block", kv[3]["k"][0], okv[3].k, 0.0625, 0.9999)
