@@ -152,16 +152,18 @@ def synthetic_inputs(cfg_dims, frames, lh, lw, noise_seed=0):
     return noise, prompt
 
 
-def cpu_reference_run(steps: int, warmup: int, sample: str = "cfg2_chunk0", budget_s: float = 0.0):
+def cpu_reference_run(steps: int, warmup: int, sample: str = "cfg2_chunk0", budget_s: float = 0.0, weights=None):
     """Times the oracle port of the reference pipeline on the host cores (native bf16 torch CPU ops). With `budget_s`,
-    stops early once another step would not fit (at least one step runs). Returns the last step's latents too."""
+    stops early once another step would not fit (at least one step runs). Returns the last step's latents too.
+    `weights`: a state dict to run with (the in-line leg passes the GPU arm's own random-init weights, so that the two arms
+    of one run compute the same function); default: the oracle's seeded random init of the same architecture."""
     from oracle import causal_wan_oracle as O
     from oracle import cpu_port
     dims, frames, lh, lw = WORKLOADS[sample]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = O.WanConfig(**dims)
-    w = O.make_weights(cfg, seed=0)
+    w = weights if weights is not None else O.make_weights(cfg, seed=0)
     noise, prompt = synthetic_inputs(dims, frames, lh, lw)
     times, latents, t_begin = [], None, time.perf_counter()
     for i in range(warmup + steps):
@@ -275,8 +277,9 @@ def run_chain(args, rank, world, device, deadline):
     from tools.chain_bench import ChainBench, limiter_of
     cb = ChainBench(device, model="14B", layers=args.chain_layers, sampling_steps=args.chain_steps, vae_connect=not args.chain_no_vae)
     t0 = time.perf_counter()
-    # untimed pass over every rank: communicators, tensor maps, KV caches, VAE workspaces (one 2-step segment per slot)
-    cb.run(1, world // cb.lanes, sampling_steps=2, warm=True)
+    # untimed pass over every rank: communicators, tensor maps, KV caches, VAE workspaces (2-step segments, one more than
+    # there are slots, so that every slot - slot 0 included - has received anchors and run the VAE connect once)
+    cb.run(1, world // cb.lanes + 1, sampling_steps=2, warm=True)
     torch.cuda.synchronize()
     warm_s = time.perf_counter() - t0
     records, skipped = [], []
@@ -474,7 +477,9 @@ def run_ours(args):
     # CPU arm (rank 0 of a 1-GPU run): bounded sample of the same workload + parity of the GPU path against its output
     if world == 1 and not args.no_cpu_baseline:
         sample = "cfg2_chunk0" if args.cpu_sample == "same" else args.cpu_sample
-        r = cpu_reference_run(steps=1, warmup=0, sample=sample)
+        same_arch = WORKLOADS[sample][0] == dims
+        r = cpu_reference_run(steps=1, warmup=0, sample=sample,
+                              weights={k: v.detach().cpu() for k, v in model.state_dict().items()} if same_arch else None)
         out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"], "ms": r["ms"]}
         if sample == "cfg2_chunk0" and args.workload == "cfg2":
             out["parity"].update(chunk0_parity(pipe, holder, device, r["latents"]))

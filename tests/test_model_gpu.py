@@ -250,7 +250,7 @@ def test_golden_cfg2_pipeline_full_depth():
     trace, x0s, latents = run_with_trace(pipe, noise, eps)
     assert len(trace) == len(fix["trace"]) == 35
     for got, ref in zip(trace, fix["trace"]):
-        assert (got["current_start"], got["timestep"], got["global_end"], got["local_end"]) == \\
+        assert (got["current_start"], got["timestep"], got["global_end"], got["local_end"]) == \
             (ref["current_start"], ref["timestep"], ref["global_end"], ref["local_end"]) and got["all_equal"]
     sub = fix["sub"]
     for call, ref in zip(fix["x0_calls"], fix["x0_sub"]):
