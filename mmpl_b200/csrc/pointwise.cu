@@ -32,6 +32,24 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
                     pack_bf16x2(f[6], f[7]));
 }
 
+// Rounds two fp32 values to bf16 and back with ONE conversion instruction (cvt.rn.bf16x2.f32) plus two integer ops,
+// instead of one conversion each: the HBM-bound kernels of this file were bound by the conversion pipe, not by memory
+// (ncu: pipe_xu 55-68 % of peak at 2-3 TB/s), because every rounding point of the reference costs a conversion.
+__device__ __forceinline__ void round2(float& a, float& b) {
+  const uint32_t p = pack_bf16x2(a, b);
+  a = bf16_lo(p);
+  b = bf16_hi(p);
+}
+
+// fp32 -> fp64 without the conversion pipe: re-bias the exponent with integer ops (exact for every normal float;
+// zeros, subnormals, infinities and NaNs take the conversion instruction).
+__device__ __forceinline__ double widen(float f) {
+  const uint32_t u = __float_as_uint(f);
+  if (((u >> 23) & 0xFFu) - 1u >= 254u) return static_cast<double>(f);
+  return __hiloint2double(static_cast<int>((u & 0x80000000u) | (((u & 0x7FFFFFFFu) >> 3) + 0x38000000u)),
+                          static_cast<int>(u << 29));
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (eps, no affine) followed by adaLN modulation, or LayerNorm with affine weight/bias.
 //   modulated (causal_model.py:305,318): out = bf16( bf16( bf16(LN(x)) * bf16(1 + scale_f) ) + shift_f )
@@ -93,14 +111,20 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
     unpack8(v[i], f);
     unpack8(kPrefetch ? av[i] : __ldg(a_ptr + lane + 32 * i), a);
     unpack8(kPrefetch ? bv[i] : __ldg(b_ptr + lane + 32 * i), b);
+    if (AFFINE) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float n = (f[j] - mean) * rstd;
-      if (AFFINE) {
-        f[j] = __fadd_rn(__fmul_rn(n, a[j]), b[j]);
-      } else {
-        const float s1 = bf16_round(1.0f + a[j]);
-        f[j] = bf16_round(bf16_round(n) * s1) + b[j];
+      for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(__fmul_rn((f[j] - mean) * rstd, a[j]), b[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {  // two elements per conversion instruction at every rounding point
+        float n0 = (f[j] - mean) * rstd, n1 = (f[j + 1] - mean) * rstd;
+        float s0 = 1.0f + a[j], s1 = 1.0f + a[j + 1];
+        round2(n0, n1);
+        round2(s0, s1);
+        float m0 = n0 * s0, m1 = n1 * s1;
+        round2(m0, m1);
+        f[j] = m0 + b[j];
+        f[j + 1] = m1 + b[j + 1];
       }
     }
     orow[lane + 32 * i] = pack8(f);
@@ -128,7 +152,12 @@ __device__ __forceinline__ void rmsnorm_row(uint4 (&v)[NCH], const __nv_bfloat16
     unpack8(v[i], f);
     unpack8(__ldg(wp + lane + 32 * i), g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = bf16_round(bf16_round(f[j] * r) * g[j]);
+    for (int j = 0; j < 8; j += 2) {
+      float t0 = f[j] * r, t1 = f[j + 1] * r;
+      round2(t0, t1);
+      f[j] = t0 * g[j];          // rounded by the pack below
+      f[j + 1] = t1 * g[j + 1];
+    }
     v[i] = pack8(f);
   }
 }
@@ -178,8 +207,8 @@ __device__ __forceinline__ void rope_row(uint4 (&v)[NCH], const double2* __restr
       const int pi = pair0 + j;
       const int pos = pi < 22 ? pt : (pi < 43 ? ph : pw);
       const double2 cs = __ldg(tab + pos * 64 + pi);
-      const double re = static_cast<double>(f[2 * j]);
-      const double im = static_cast<double>(f[2 * j + 1]);
+      const double re = widen(f[2 * j]);
+      const double im = widen(f[2 * j + 1]);
       const double ore = __dsub_rn(__dmul_rn(re, cs.x), __dmul_rn(im, cs.y));
       const double oim = __dadd_rn(__dmul_rn(re, cs.y), __dmul_rn(im, cs.x));
       f[2 * j] = __double2float_rn(ore);

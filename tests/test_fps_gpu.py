@@ -72,10 +72,11 @@ def test_fps_model_matches_reference_golden():
 
 TINY = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
 # Tolerance of a whole guided rollout (bf16, 3 UniPC steps x CFG 5.0 per stage, 4-5 stages feeding each other through the KV
-# cache): per stage max-abs 0.25 and cosine 0.999 against the oracle-driven trajectory. One forward agrees to max-abs 0.0625 /
-# cosine 0.9999 (tests above); the CFG extrapolation u + 5 (c - u) multiplies a difference between the two branches by up to
-# 9 per step, and later stages attend to the K/V earlier ones wrote.
-STAGE_MAX_ABS, STAGE_MIN_COS = 0.25, 0.999
+# cache): per stage max-abs 0.125 and cosine 0.9999 against the oracle-driven trajectory (measured on B200: 0.03-0.0625 /
+# 0.99998, profiles/r02_parity_gpu.log). One forward agrees to max-abs 0.0625 / cosine 0.9999 (tests above); the CFG
+# extrapolation u + 5 (c - u) multiplies a difference between the two branches by up to 9 per step, and later stages attend
+# to the K/V earlier ones wrote.
+STAGE_MAX_ABS, STAGE_MIN_COS = 0.125, 0.9999
 
 
 def _text_vae(prompt):
