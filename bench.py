@@ -51,9 +51,16 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry exactly one JSON line, whatever libraries print (NCCL's version banner goes to fd 1 when NCCL_DEBUG is
+# VERSION or higher and no NCCL_DEBUG_FILE is set): fd 1 is pointed at stderr for the whole run and the line is written to
+# the saved descriptor by emit().
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(record: dict) -> None:
+    os.write(_STDOUT_FD, (json.dumps(record) + "\n").encode())
+
 
 METRIC = "denoised_latent_frames_per_s"
 UNIT = "latent frames/s"
@@ -188,7 +195,7 @@ def run_reference(args):
     sample = args.workload if args.cpu_sample == "same" else args.cpu_sample
     r = cpu_reference_run(max(1, args.steps), 0, sample, budget_s=args.cpu_budget)
     same = sample == args.workload
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
         "warmup": 0, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
@@ -199,7 +206,7 @@ def run_reference(args):
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                          "steps": r["steps"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------------------ our arm
@@ -501,7 +508,7 @@ def run_ours(args):
             out["chain"] = chain
     if rank == 0:
         out["wall_s"] = round(time.perf_counter() - t_start, 1)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
