@@ -54,6 +54,7 @@ sys.path.insert(0, ROOT)
 # stdout must carry exactly one JSON line, whatever libraries print (NCCL's version banner goes to fd 1 when NCCL_DEBUG is
 # VERSION or higher and no NCCL_DEBUG_FILE is set): fd 1 is pointed at stderr for the whole run and the line is written to
 # the saved descriptor by emit().
+os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
 _STDOUT_FD = os.dup(1)
 os.dup2(2, 1)
 

@@ -126,14 +126,18 @@ class AnchorChannel:
         if dst == self.rank:
             self._local[segment + 1] = payload.clone()
             return
-        self._pending.append((dist.isend(payload, dst=self._global(dst), group=self.group, tag=segment + 1), payload))
+        # batched form (one-op batch): on NCCL an unbatched send on an eagerly initialised group is ordered like a collective
+        # against everything else on that group; a batch is an independent point-to-point transfer
+        works = dist.batch_isend_irecv([dist.P2POp(dist.isend, payload, self._global(dst), self.group, segment + 1)])
+        self._pending.extend((w, payload) for w in works)
 
     def recv(self, segment: int, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Tensor:
         src = producer_of(segment - 1, self.world, self.lanes, self.lane)
         if src == self.rank:
             return self._local.pop(segment)
         buf = torch.empty(tuple(shape), dtype=dtype, device=device)
-        dist.recv(buf, src=self._global(src), group=self.group, tag=segment)
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, buf, self._global(src), self.group, segment)]):
+            w.wait()   # NCCL: orders the current stream after the transfer, the host does not block
         return buf
 
     def flush(self) -> None:
