@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MMPL_ABI_VERSION 2
+#define MMPL_ABI_VERSION 3
 
 enum {
   MMPL_OK = 0,
@@ -64,15 +64,18 @@ int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
  * nn.Conv2d(3x3, padding 1) / 1x1 convolutions of the same file (:75-81, :233-235) -- the contraction that carries the
  * VAE "segment connect" either side of the anchor hand-off (Wan_fps_inference_parallel_4gpu_20s.py:191-205;
  * SURVEY.md 8(f) row 2). Layouts (bf16):
- *   in       [(T + KT - 1)][H + 2][W + 2][Cin]  one-pixel zero halo; the KT - 1 leading frames are the causal history
- *                                               (zeros, or the frames `feat_cache` carries between chunks, vae.py:197-209)
- *   w_packed [Cout][KT*KH*KW][Cin64]            Cin64 = Cin rounded up to a multiple of 64, zero padded; taps ordered
- *                                               dt, dh, dw (= weight.permute(0,2,3,4,1) of the reference parameter)
+ *   in       [history + T][H + 2][W + 2][Cin]   one-pixel zero halo; `history` in 0..KT-1 = carried frames stored in front
+ *                                               of the T frames (what `feat_cache` carries between chunks, vae.py:197-209);
+ *                                               the remaining KT-1-history causal padding frames are implicit zeros
+ *   w_packed KW = 1: [Cout][KT*KH][Cin64]       Cin64 = Cin rounded up to a multiple of 64, zero padded
+ *            KW = 3: [Cout][KT*KH][K3]          K3 = 3*Cin rounded up to 64; inside a span the order is (dw, c): the three
+ *                                               dw taps of an image row are read as ONE contiguous run of the grid
+ *                                               (= weight.permute(0,2,3,4,1) of the reference parameter, rows padded)
  *   bias     [Cout] or NULL;  residual: NULL or a tensor laid out like `out` (ResidualBlock's `x + h`, vae.py:213)
- *   out      [T][H + 2][W + 2][Cout]            only interior positions are written: a zeroed buffer keeps its halo
+ *   out      [T][H + 2][W + 2][Cout]            every position is written: interior = convolution, halo = 0
  * Cin and Cout must be multiples of 8 (pad channels in the layout); KT, KH = KW in {1, 3}. */
 int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
-                   int W, int Cin, int Cout, int KT, int KH, int KW, void* stream);
+                   int W, int Cin, int Cout, int KT, int KH, int KW, int history, void* stream);
 
 /* RMS_norm.forward (wan/modules/vae.py:39-55: F.normalize over channels * sqrt(C) * gamma), optionally followed by
  * nn.SiLU (the `RMS_norm, SiLU` pairs of ResidualBlock / the heads, vae.py:180-186,309-311,413-415), over `rows` rows of C
@@ -81,12 +84,12 @@ int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void*
 int mmpl_vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamma, int silu, void* stream);
 
 /* Upsample(scale_factor=(2,2), mode='nearest') of every frame (vae.py:58-64,75-78): in [frames][H+2][W+2][C] ->
- * out [frames][2H+2][2W+2][C]; interior positions only are written (a zeroed `out` keeps its halo). */
+ * out [frames][2H+2][2W+2][C]; every position of `out` is written (halo = 0). */
 int mmpl_vae_upsample2x(const void* in, void* out, int frames, int H, int W, int C, void* stream);
 
 /* The stride-2 pick that turns a stride-1 3x3 "same" convolution of the haloed grid into the reference's
  * nn.ZeroPad2d((0,1,0,1)) + nn.Conv2d(3, stride=(2,2)) (vae.py:85-88): out interior (i, j) = in interior (2i+1, 2j+1).
- * in [frames][Hin+2][Win+2][C] -> out [frames][Hin/2+2][Win/2+2][C], interior only. */
+ * in [frames][Hin+2][Win+2][C] -> out [frames][Hin/2+2][Win/2+2][C]; every position of `out` is written (halo = 0). */
 int mmpl_vae_pick_odd(const void* in, void* out, int frames, int Hin, int Win, int C, void* stream);
 
 /* p[r, :] = softmax(scale * s[r, :]) in fp32, bf16 in and out (row pitches lds / ldp in elements): the softmax of the

@@ -13,7 +13,7 @@ from pathlib import Path
 from . import _build
 
 _LIB = None
-ABI_VERSION = 2  # == MMPL_ABI_VERSION in include/mmpl_b200.h (tests/test_abi.py checks the header)
+ABI_VERSION = 3  # == MMPL_ABI_VERSION in include/mmpl_b200.h (tests/test_abi.py checks the header)
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
 c_int_p = C.POINTER(C.c_int)
@@ -61,7 +61,7 @@ SIGNATURES = {
     "mmpl_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mmpl_conv3d_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_int, c_int, c_void_p]),
+                               c_int, c_int, c_int, c_void_p]),
     "mmpl_vae_norm_act": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "mmpl_vae_upsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmpl_vae_pick_odd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

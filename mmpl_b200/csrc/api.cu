@@ -135,8 +135,8 @@ int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
 }
 
 int mmpl_conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
-                   int W, int Cin, int Cout, int KT, int KH, int KW, void* stream) {
-  COUNTED(conv3d_cl(in, w_packed, bias, out, residual, T, H, W, Cin, Cout, KT, KH, KW, static_cast<cudaStream_t>(stream)));
+                   int W, int Cin, int Cout, int KT, int KH, int KW, int history, void* stream) {
+  COUNTED(conv3d_cl(in, w_packed, bias, out, residual, T, H, W, Cin, Cout, KT, KH, KW, history, static_cast<cudaStream_t>(stream)));
 }
 
 int mmpl_vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamma, int silu, void* stream) {

@@ -91,11 +91,15 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsOf<CONV>::typ
                                               int64_t part_stride = 0) {
   constexpr bool kHasRes = (EPI == MMPL_EPI_BIAS_RES || EPI == MMPL_EPI_BIAS_GATE_RES);
   bool row_ok = row < p.M;
+  bool halo_row = false;
   if constexpr (CONV) {
-    // rows are positions of the zero-haloed grid: the halo stays zero (never written), interior rows are stored
+    // rows are positions of the zero-haloed grid: interior rows get the convolution, halo rows are written as zeros, so
+    // the output is a valid padded input of the next layer whatever the buffer held before (no fill pass anywhere)
     const int wp = row % p.conv_wp;
     const int hp = (row / p.conv_wp) % p.conv_hp;
-    row_ok = row_ok && wp >= 1 && wp < p.conv_wp - 1 && hp >= 1 && hp < p.conv_hp - 1;
+    const bool interior = wp >= 1 && wp < p.conv_wp - 1 && hp >= 1 && hp < p.conv_hp - 1;
+    halo_row = row_ok && !interior;
+    row_ok = row_ok && interior;
   }
   const __nv_bfloat16* gate_row = nullptr;
   if (EPI == MMPL_EPI_BIAS_GATE_RES && row_ok)
@@ -204,6 +208,11 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsOf<CONV>::typ
           if (have[1]) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
         }
       }
+    } else if (CONV && halo_row && col0 < p.N) {
+      __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (col0 + g * 8 < p.N) *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(0, 0, 0, 0);
     }
   }
 }
@@ -838,13 +847,19 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
 // ------------------------------------------------------------------------------------------------------------------
 // Causal 3-D convolution as a tap-GEMM (wan/modules/vae.py:16-36 CausalConv3d, stride 1; also its per-frame Conv2d
 // 3x3 and the 1x1 convolutions), channels-last:
-//   in  [(T + KT - 1)][H + 2][W + 2][Cin]   bf16, zero halo of one pixel; the KT-1 leading frames are the causal
-//                                            history (zeros for the first chunk, carried frames otherwise)
-//   w   [Cout][KT * KH * KW][Cin64]          bf16, Cin64 = Cin rounded up to 64 (zero padded), taps dt-major
-//   out [T][H + 2][W + 2][Cout]              bf16; interior positions only are written
-// out(t, h, w, :) = bias + sum_taps in(t + dt, h + dh - KH/2, w + dw - KW/2, :) . w[:, tap, :]  (+ residual)
+//   in  [history + T][H + 2][W + 2][Cin]    bf16, one-pixel halo of zeros; `history` (0..KT-1) carried frames in front,
+//                                            the KT-1-history frames before them are zeros that are never stored: their
+//                                            rows have negative coordinates, which TMA fills with zeros
+//   out [T][H + 2][W + 2][Cout]              bf16; interior positions = the convolution, halo positions = 0
+// out(t, h, w, :) = bias + sum_taps in(t + dt - (KT-1), h + dh - KH/2, w + dw - KW/2, :) . w[:, tap, :]  (+ residual)
 // Every grid position (halo included) is one GEMM row; a tap is a row shift of the same A matrix, so the A operand
 // is read in place by TMA: no im2col buffer. The halo rows cost (H+2)(W+2)/(HW) - 1 extra MMA work (0.7 % at 480x832).
+// K layout. KW = 1: one K span of Cin per tap. KW = 3: the three dw taps of one (dt, dh) are three CONSECUTIVE rows of
+// the channels-last grid, i.e. one contiguous span of 3*Cin elements starting at row r - 1; the A tensor map describes
+// that directly (row pitch Cin, row length 3*Cin: rows overlap), so K per (dt, dh) is 3*Cin rounded up to 64 instead of
+// three times Cin rounded up to 64: 320 instead of 384 at the VAE's 96-channel level, 64 instead of 192 for its 3- and
+// 16-channel ends.
+//   w   KW = 1: [Cout][KT*KH][Cin64]; KW = 3: [Cout][KT*KH][pad64(3*Cin)] with (dw, c) order inside a span; bf16, zero padded
 template <int BN, int EPI>
 static int launch_conv(const CUtensorMap* ma, const CUtensorMap* mb, ConvGemmParams p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -864,7 +879,7 @@ static int launch_conv(const CUtensorMap* ma, const CUtensorMap* mb, ConvGemmPar
 }
 
 int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
-              int W, int Cin, int Cout, int KT, int KH, int KW, cudaStream_t stream) {
+              int W, int Cin, int Cout, int KT, int KH, int KW, int history, cudaStream_t stream) {
   MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "conv3d: requires an sm_100 device");
   MMPL_CHECK(in && w_packed && out, MMPL_ERR_ARG, "conv3d: null argument");
   MMPL_CHECK(T > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, MMPL_ERR_SHAPE, "conv3d: bad shape");
@@ -872,39 +887,50 @@ int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out,
              "conv3d: channel counts must be multiples of 8 (pad the layout): Cin=%d Cout=%d", Cin, Cout);
   MMPL_CHECK((KT == 1 || KT == 3) && (KH == 1 || KH == 3) && KH == KW, MMPL_ERR_SHAPE,
              "conv3d: kernel %dx%dx%d not supported (1 or 3 per axis, square)", KT, KH, KW);
+  MMPL_CHECK(history >= 0 && history <= KT - 1, MMPL_ERR_ARG, "conv3d: history=%d frames, the kernel takes 0..%d", history, KT - 1);
   const int Hp = H + 2, Wp = W + 2;
   const int64_t rows_out = static_cast<int64_t>(T) * Hp * Wp;
-  const int64_t rows_in = static_cast<int64_t>(T + KT - 1) * Hp * Wp;
+  const int64_t rows_in = static_cast<int64_t>(T + history) * Hp * Wp;
   MMPL_CHECK(rows_in < (int64_t(1) << 31) - 65536, MMPL_ERR_SHAPE, "conv3d: %lld grid positions exceed the 32-bit row index",
              (long long)rows_in);
-  const int taps = KT * KH * KW;
-  const int kb_per_tap = (Cin + kBK - 1) / kBK;
-  const int cin64 = kb_per_tap * kBK;
+  const bool rowpack = KW == 3;
+  const int spans = rowpack ? KT * KH : KT * KH * KW;     // K spans ("taps" of the kernel's k loop)
+  const int span = rowpack ? 3 * Cin : Cin;
+  const int kb_per_span = (span + kBK - 1) / kBK;
 
   ConvGemmParams p{};
   p.M = static_cast<int>(rows_out);
   p.N = Cout;
-  p.K = taps * cin64;
+  p.K = spans * kb_per_span * kBK;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = Cout;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.res = static_cast<const __nv_bfloat16*>(residual);
   p.ldr = Cout;
   p.rows_per_frame = 1;
-  p.conv_kb_per_tap = kb_per_tap;
+  p.conv_kb_per_tap = kb_per_span;
   p.conv_hp = Hp;
   p.conv_wp = Wp;
   int i = 0;
   for (int dt = 0; dt < KT; ++dt)
-    for (int dh = 0; dh < KH; ++dh)
-      for (int dw = 0; dw < KW; ++dw) p.conv_tap_off[i++] = (dt * Hp + (dh - KH / 2)) * Wp + (dw - KW / 2);
+    for (int dh = 0; dh < KH; ++dh) {
+      const int frame_row = ((dt - (KT - 1) + history) * Hp + (dh - KH / 2)) * Wp;  // first row of the tap's image row
+      if (rowpack) {
+        p.conv_tap_off[i++] = frame_row - 1;
+      } else {
+        for (int dw = 0; dw < KW; ++dw) p.conv_tap_off[i++] = frame_row + (dw - KW / 2);
+      }
+    }
 
-  int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : ((Cout <= 256 || Cout % 256 == 0) ? 256 : 128));
-  // Opt-in (MMPL_CONV_BN96=1, not yet run on a GPU): 96-wide tiles (UMMA N = 96) for the 96- and 192-channel levels, which
-  // otherwise leave a quarter of a 128- / 256-wide tile's columns empty.
-  static const bool bn96 = getenv("MMPL_CONV_BN96") != nullptr && atoi(getenv("MMPL_CONV_BN96")) != 0;
-  if (bn96 && (Cout == 96 || Cout == 192)) bn = 96;
-  const CUtensorMap* ma = get_tensor_map_bf16(in, static_cast<uint64_t>(rows_in), Cin, Cin, kBM);
+  // tile width: 96 for the VAE's 96- and 192-channel levels (UMMA N = 96; a 128- / 256-wide tile would compute a quarter
+  // of its columns for nothing), otherwise the narrowest of 64 / 128 / 256 that holds Cout or divides it
+  int bn = Cout <= 64 ? 64 : ((Cout == 96 || Cout == 192) ? 96 : (Cout <= 128 ? 128 : ((Cout <= 256 || Cout % 256 == 0) ? 256 : 128)));
+  static const bool no_bn96 = getenv("MMPL_CONV_BN96") != nullptr && atoi(getenv("MMPL_CONV_BN96")) == 0;  // A/B switch
+  if (no_bn96 && bn == 96) bn = Cout <= 128 ? 128 : 256;
+  // KW = 3: rows of 3*Cin elements that start Cin apart (overlapping); the last two grid positions are left out of the
+  // map so that no row of it reaches past the buffer (they are halo positions, and TMA zero-fills them as operands)
+  const CUtensorMap* ma = rowpack ? get_tensor_map_bf16(in, static_cast<uint64_t>(rows_in - 2), 3 * Cin, Cin, kBM)
+                                  : get_tensor_map_bf16(in, static_cast<uint64_t>(rows_in), Cin, Cin, kBM);
   const CUtensorMap* mb = get_tensor_map_bf16(w_packed, Cout, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.K), bn);
   if (!ma || !mb) return MMPL_ERR_CUDA;
   const bool res = residual != nullptr;

@@ -13,7 +13,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
 
 // Causal 3-D convolution as a tap-GEMM over a zero-haloed channels-last grid (gemm_tcgen05.cu: conv3d_cl).
 int conv3d_cl(const void* in, const void* w_packed, const void* bias, void* out, const void* residual, int T, int H,
-              int W, int Cin, int Cout, int KT, int KH, int KW, cudaStream_t stream);
+              int W, int Cin, int Cout, int KT, int KH, int KW, int history, cudaStream_t stream);
 
 // vae_pointwise.cu: HBM-bound kernels of the VAE segment connect on the zero-haloed channels-last grid
 int vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamma, int silu, cudaStream_t st);

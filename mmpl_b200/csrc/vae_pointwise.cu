@@ -23,6 +23,11 @@ __device__ __forceinline__ void unpack8v(const uint4& v, float (&f)[8]) {
     f[2 * i + 1] = bf16_hi(w[i]);
   }
 }
+__device__ __forceinline__ void round2v(float& a, float& b) {  // both to bf16 and back with one cvt.rn.bf16x2.f32
+  const uint32_t p = pack_bf16x2(a, b);
+  a = bf16_lo(p);
+  b = bf16_hi(p);
+}
 __device__ __forceinline__ uint4 pack8v(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
@@ -65,6 +70,16 @@ vae_norm_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float n = fmaxf(bf16_round(sqrtf(sq)), 1e-12f);
   if (!row_ok) return;
+  // x / n with n shared by the row: q0 = x * RN(1/n), corrected with the exact remainder (two FMAs). For bf16 operands this
+  // is the correctly rounded fp32 quotient - checked exhaustively over all 2^7 x 2^7 mantissa pairs - so the bf16 result
+  // equals the reference's division; results outside the normal range take the division instruction.
+  const float rn = __frcp_rn(n);
+  auto quotient = [&](float a) {
+    const float q0 = __fmul_rn(a, rn);
+    const float q = __fmaf_rn(__fmaf_rn(-q0, n, a), rn, q0);
+    const float aq = fabsf(q0);
+    return (aq == 0.f || (aq >= 1e-30f && aq <= 1e30f)) ? q : __fdiv_rn(a, n);
+  };
   uint4* orow = reinterpret_cast<uint4*>(out + row * C);
   const uint4* gp = reinterpret_cast<const uint4*>(gamma);
 #pragma unroll
@@ -75,58 +90,72 @@ vae_norm_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     unpack8v(v[i], f);
     unpack8v(__ldg(gp + c), g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = bf16_round(f[j] / n);
-      y = bf16_round(y * scale);
-      y = bf16_round(y * g[j]);
-      if (silu) y = y / (1.0f + expf(-y));
-      f[j] = y;
+    for (int j = 0; j < 8; j += 2) {  // two elements per conversion instruction at every rounding point
+      float y0 = quotient(f[j]), y1 = quotient(f[j + 1]);
+      round2v(y0, y1);
+      y0 *= scale;
+      y1 *= scale;
+      round2v(y0, y1);
+      y0 *= g[j];
+      y1 *= g[j + 1];
+      if (silu) {
+        round2v(y0, y1);
+        y0 = y0 / (1.0f + expf(-y0));
+        y1 = y1 / (1.0f + expf(-y1));
+      }
+      f[j] = y0;          // rounded by the pack below
+      f[j + 1] = y1;
     }
     orow[c] = pack8v(f);
   }
 }
 
-// Upsample(scale_factor=(2,2), mode='nearest') per frame (vae.py:58-64,75-78): out interior (2i+a, 2j+b) = in interior (i, j).
-// One thread per (output position, 16-byte chunk).
+// Upsample(scale_factor=(2,2), mode='nearest') per frame (vae.py:58-64,75-78): out interior (2i+a, 2j+b) = in interior (i, j),
+// out halo = 0 (every position of `out` is written: no fill pass). One thread per (output position, 16-byte chunk).
 __global__ void __launch_bounds__(256)
 vae_upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int frames, int H, int W, int chunks) {
   pdl_wait();
   pdl_launch_dependents();
-  const int64_t total = static_cast<int64_t>(frames) * (2 * H) * (2 * W) * chunks;
+  const int Ho = 2 * H + 2, Wo = 2 * W + 2;
+  const int64_t total = static_cast<int64_t>(frames) * Ho * Wo * chunks;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % chunks);
     int64_t r = i / chunks;
-    const int ow = static_cast<int>(r % (2 * W));
-    r /= 2 * W;
-    const int oh = static_cast<int>(r % (2 * H));
-    const int f = static_cast<int>(r / (2 * H));
-    const int64_t src = ((static_cast<int64_t>(f) * (H + 2) + (oh >> 1) + 1) * (W + 2) + (ow >> 1) + 1) * chunks + c;
-    const int64_t dst = ((static_cast<int64_t>(f) * (2 * H + 2) + oh + 1) * (2 * W + 2) + ow + 1) * chunks + c;
-    out[dst] = __ldg(in + src);
+    const int ow = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oh = static_cast<int>(r % Ho);
+    const int f = static_cast<int>(r / Ho);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ow >= 1 && ow <= 2 * W && oh >= 1 && oh <= 2 * H)
+      v = __ldg(in + ((static_cast<int64_t>(f) * (H + 2) + ((oh - 1) >> 1) + 1) * (W + 2) + ((ow - 1) >> 1) + 1) * chunks + c);
+    out[i] = v;
   }
 }
 
 // The stride-2 pick that turns a stride-1 "same" 3x3 convolution into nn.ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2)
 // (vae.py:85-88): the strided convolution's output (i, j) has its window centred on input (2i+1, 2j+1), whose bottom /
-// right neighbours beyond the image are the halo's zeros. out interior (i, j) = in interior (2i+1, 2j+1); H, W = output size.
+// right neighbours beyond the image are the halo's zeros. out interior (i, j) = in interior (2i+1, 2j+1), out halo = 0;
+// H, W = output size.
 __global__ void __launch_bounds__(256)
 vae_pick_odd_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int frames, int H, int W, int Hin, int Win,
                     int chunks) {
   pdl_wait();
   pdl_launch_dependents();
-  const int64_t total = static_cast<int64_t>(frames) * H * W * chunks;
+  const int Ho = H + 2, Wo = W + 2;
+  const int64_t total = static_cast<int64_t>(frames) * Ho * Wo * chunks;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % chunks);
     int64_t r = i / chunks;
-    const int ow = static_cast<int>(r % W);
-    r /= W;
-    const int oh = static_cast<int>(r % H);
-    const int f = static_cast<int>(r / H);
-    const int64_t src = ((static_cast<int64_t>(f) * (Hin + 2) + 2 * oh + 2) * (Win + 2) + 2 * ow + 2) * chunks + c;
-    const int64_t dst = ((static_cast<int64_t>(f) * (H + 2) + oh + 1) * (W + 2) + ow + 1) * chunks + c;
-    out[dst] = __ldg(in + src);
+    const int ow = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oh = static_cast<int>(r % Ho);
+    const int f = static_cast<int>(r / Ho);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ow >= 1 && ow <= W && oh >= 1 && oh <= H)
+      v = __ldg(in + ((static_cast<int64_t>(f) * (Hin + 2) + 2 * oh) * (Win + 2) + 2 * ow) * chunks + c);
+    out[i] = v;
   }
 }
 
@@ -215,7 +244,7 @@ int vae_norm_act(const void* x, void* out, int64_t rows, int C, const void* gamm
 int vae_upsample2x(const void* in, void* out, int frames, int H, int W, int C, cudaStream_t st) {
   MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "vae_upsample2x: requires an sm_100 device");
   MMPL_CHECK(in && out && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, MMPL_ERR_SHAPE, "vae_upsample2x: bad shape");
-  const int64_t total = static_cast<int64_t>(frames) * 4 * H * W * (C / 8);
+  const int64_t total = static_cast<int64_t>(frames) * (2 * H + 2) * (2 * W + 2) * (C / 8);
   MMPL_CUDA_LAUNCH(launch_kernel(vae_upsample2x_kernel, grid_1d(total, 256), 256, 0, st, static_cast<const uint4*>(in),
                                  static_cast<uint4*>(out), frames, H, W, C / 8));
   MMPL_CUDA(cudaGetLastError());
@@ -226,7 +255,7 @@ int vae_pick_odd(const void* in, void* out, int frames, int Hin, int Win, int C,
   MMPL_CHECK(device_is_sm100(), MMPL_ERR_ARCH, "vae_pick_odd: requires an sm_100 device");
   MMPL_CHECK(in && out && frames > 0 && Hin > 1 && Win > 1 && C > 0 && C % 8 == 0, MMPL_ERR_SHAPE, "vae_pick_odd: bad shape");
   const int H = Hin / 2, W = Win / 2;  // floor((Hin + 1 - 3) / 2) + 1 outputs of the padded stride-2 convolution
-  const int64_t total = static_cast<int64_t>(frames) * H * W * (C / 8);
+  const int64_t total = static_cast<int64_t>(frames) * (H + 2) * (W + 2) * (C / 8);
   MMPL_CUDA_LAUNCH(launch_kernel(vae_pick_odd_kernel, grid_1d(total, 256), 256, 0, st, static_cast<const uint4*>(in),
                                  static_cast<uint4*>(out), frames, H, W, Hin, Win, C / 8));
   MMPL_CUDA(cudaGetLastError());

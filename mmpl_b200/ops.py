@@ -236,64 +236,75 @@ def add_noise(x0: torch.Tensor, noise: torch.Tensor, sigma: torch.Tensor) -> tor
 # ------------------------------------------------------------------------------------ VAE segment connect
 
 def pack_conv_weight(weight: torch.Tensor) -> torch.Tensor:
-    """Reference conv parameter [Cout, Cin, KT, KH, KW] (or [Cout, Cin, KH, KW] of a per-frame Conv2d) -> the tap-major
-    layout mmpl_conv3d_cl reads: [Cout8, KT*KH*KW, Cin64] bf16, Cin zero-padded to a multiple of 64 and Cout to a
-    multiple of 8. One-time layout transform of the weights (no arithmetic)."""
+    """Reference conv parameter [Cout, Cin, KT, KH, KW] (or [Cout, Cin, KH, KW] of a per-frame Conv2d) -> the layout
+    mmpl_conv3d_cl reads, bf16, Cout padded to a multiple of 8 and Cin to a multiple of 8:
+      KW = 1: [Cout8, KT*KH, Cin64]              one K span of Cin (zero-padded to 64) per tap
+      KW = 3: [Cout8, KT*KH, pad64(3 * Cin8)]    one K span per (dt, dh): the three dw taps side by side, (dw, c) order,
+                                                 because they are one contiguous run of the channels-last grid
+    One-time layout transform of the weights (no arithmetic)."""
     if weight.dim() == 4:
         weight = weight.unsqueeze(2)
     cout, cin, kt, kh, kw = weight.shape
-    cin64, cout8 = -(-cin // 64) * 64, -(-cout // 8) * 8
-    w = weight.permute(0, 2, 3, 4, 1).reshape(cout, kt * kh * kw, cin)
+    cin8, cout8 = -(-cin // 8) * 8, -(-cout // 8) * 8
+    w = weight.permute(0, 2, 3, 4, 1).to(torch.bfloat16)                      # [cout, kt, kh, kw, cin]
+    if kw == 3:
+        span = -(-3 * cin8 // 64) * 64
+        packed = torch.zeros((cout8, kt * kh, span), dtype=torch.bfloat16, device=weight.device)
+        rows = torch.zeros((cout, kt * kh, 3, cin8), dtype=torch.bfloat16, device=weight.device)
+        rows[..., :cin] = w.reshape(cout, kt * kh, 3, cin)
+        packed[:cout, :, :3 * cin8] = rows.reshape(cout, kt * kh, 3 * cin8)
+        return packed
+    cin64 = -(-cin // 64) * 64
     packed = torch.zeros((cout8, kt * kh * kw, cin64), dtype=torch.bfloat16, device=weight.device)
-    packed[:cout, :, :cin] = w.to(torch.bfloat16)
+    packed[:cout, :, :cin] = w.reshape(cout, kt * kh * kw, cin)
     return packed
 
 
-def to_haloed(x: torch.Tensor, lead: int = 2, channels: Optional[int] = None) -> torch.Tensor:
-    """[C, T, H, W] -> channels-last grid [lead + T, H + 2, W + 2, C8] with a zero halo and `lead` zero frames in front
-    (the layout the VAE kernels keep their activations in; C padded to a multiple of 8 or to `channels`)."""
+def to_haloed(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    """[C, T, H, W] -> channels-last grid [T, H + 2, W + 2, C8] with a zero halo (the layout the VAE kernels keep their
+    activations in; C padded to a multiple of 8 or to `channels`). The causal padding frames are not stored: the
+    convolution reads them as zeros (see mmpl_conv3d_cl `history`)."""
     c, t, h, w = x.shape
     c8 = channels if channels is not None else -(-c // 8) * 8
-    g = torch.zeros((lead + t, h + 2, w + 2, c8), dtype=torch.bfloat16, device=x.device)
-    g[lead:, 1:-1, 1:-1, :c] = x.permute(1, 2, 3, 0).to(torch.bfloat16)
+    g = torch.zeros((t, h + 2, w + 2, c8), dtype=torch.bfloat16, device=x.device)
+    g[:, 1:-1, 1:-1, :c] = x.permute(1, 2, 3, 0).to(torch.bfloat16)
     return g
 
 
-def from_haloed(g: torch.Tensor, lead: int = 2, channels: Optional[int] = None) -> torch.Tensor:
-    """Inverse of to_haloed: [lead + T, H + 2, W + 2, C8] -> [C, T, H, W]."""
+def from_haloed(g: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    """Inverse of to_haloed: [T, H + 2, W + 2, C8] -> [C, T, H, W]."""
     c = g.shape[3] if channels is None else channels
-    return g[lead:, 1:-1, 1:-1, :c].permute(3, 0, 1, 2).contiguous()
+    return g[:, 1:-1, 1:-1, :c].permute(3, 0, 1, 2).contiguous()
 
 
 @_on_device
 def conv3d_causal_cl(grid: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], kernel: Sequence[int],
-                     lead: int = 2, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     history: int = 0, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """CausalConv3d.forward (wan/modules/vae.py:16-36), stride 1, on a haloed channels-last grid (see to_haloed).
-    `grid` holds `lead` >= KT-1 history frames in front of its T frames; the result is a grid of the same geometry
-    (same `lead`, history frames and halo zero) with Cout channels. `residual`: a grid like the result, added in the epilogue."""
+    `grid` is [history + T, H + 2, W + 2, Cin]: `history` (0..KT-1) carried frames in front of the T frames to convolve,
+    zeros standing in for the rest of the causal padding. Returns [T, H + 2, W + 2, Cout] (halo written as zeros by the
+    kernel). `residual`: a grid like the result, added in the epilogue."""
     lib = _lib.load()
     _req(grid, "grid"); _req(w_packed, "w_packed")
     kt, kh, kw = (int(k) for k in kernel)
     frames, hp, wp, cin = grid.shape
-    t = frames - lead
+    t = frames - history
     cout = w_packed.shape[0]
-    if lead < kt - 1 or t <= 0:
-        raise ValueError(f"grid has {lead} leading frames, the kernel needs {kt - 1}")
-    if w_packed.shape[1] != kt * kh * kw or w_packed.shape[2] != -(-cin // 64) * 64:
+    if not 0 <= history <= kt - 1 or t <= 0:
+        raise ValueError(f"history={history} frames in a grid of {frames}; the kernel takes 0..{kt - 1}")
+    span = -(-3 * cin // 64) * 64 if kw == 3 else -(-cin // 64) * 64
+    if tuple(w_packed.shape[1:]) != (kt * kh * (1 if kw == 3 else kw), span):
         raise ValueError("w_packed does not match the grid's channels / the kernel size (see pack_conv_weight)")
+    if not grid.is_contiguous():
+        raise ValueError("grid must be contiguous")
     if out is None:
-        out = torch.zeros((frames, hp, wp, cout), dtype=torch.bfloat16, device=grid.device)
+        out = torch.empty((t, hp, wp, cout), dtype=torch.bfloat16, device=grid.device)
     if bias is not None and bias.numel() != cout:
         bias = torch.cat([bias.to(torch.bfloat16), bias.new_zeros(cout - bias.numel(), dtype=torch.bfloat16)])
-    frame = hp * wp
-    esz = 2
     if bias is not None:
         bias = bias.to(torch.bfloat16).contiguous()
-    _lib.check(lib.mmpl_conv3d_cl(
-        grid.data_ptr() + (lead - (kt - 1)) * frame * cin * esz, w_packed.data_ptr(), _p(bias),
-        out.data_ptr() + lead * frame * cout * esz,
-        None if residual is None else residual.data_ptr() + lead * frame * cout * esz,
-        t, hp - 2, wp - 2, cin, cout, kt, kh, kw, _stream()))
+    _lib.check(lib.mmpl_conv3d_cl(grid.data_ptr(), w_packed.data_ptr(), _p(bias), out.data_ptr(), _p(residual),
+                                  t, hp - 2, wp - 2, cin, cout, kt, kh, kw, history, _stream()))
     return out
 
 
@@ -320,7 +331,7 @@ def vae_upsample2x(grid: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _req(grid, "grid")
     frames, hp, wp, c = grid.shape
-    out = torch.zeros((frames, 2 * (hp - 2) + 2, 2 * (wp - 2) + 2, c), dtype=torch.bfloat16, device=grid.device)
+    out = torch.empty((frames, 2 * (hp - 2) + 2, 2 * (wp - 2) + 2, c), dtype=torch.bfloat16, device=grid.device)
     _lib.check(lib.mmpl_vae_upsample2x(grid.data_ptr(), out.data_ptr(), frames, hp - 2, wp - 2, c, _stream()))
     return out
 
@@ -331,7 +342,7 @@ def vae_pick_odd(grid: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _req(grid, "grid")
     frames, hp, wp, c = grid.shape
-    out = torch.zeros((frames, (hp - 2) // 2 + 2, (wp - 2) // 2 + 2, c), dtype=torch.bfloat16, device=grid.device)
+    out = torch.empty((frames, (hp - 2) // 2 + 2, (wp - 2) // 2 + 2, c), dtype=torch.bfloat16, device=grid.device)
     _lib.check(lib.mmpl_vae_pick_odd(grid.data_ptr(), out.data_ptr(), frames, hp - 2, wp - 2, c, _stream()))
     return out
 

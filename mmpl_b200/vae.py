@@ -4,10 +4,11 @@ decode 21 latent frames of which 4 are non-zero, keep pixel frames 8..12, re-enc
 reference's wrapper interface (`WanVAEWrapper.decode_to_pixel` / `encode_to_latent`, utils/wan_wrapper.py:74-113).
 
 B200 design:
-* activations never leave one layout: a zero-haloed channels-last grid `[2 + T, H + 2, W + 2, C]` bf16 (two leading zero
-  frames = the causal padding; the halo = the spatial padding). Every convolution of the network — 3x3x3 causal,
-  (3,1,1) temporal, per-frame 3x3, 1x1 — is one launch of the tap-GEMM tcgen05 kernel (`mmpl_conv3d_cl`) reading
-  that grid in place; bias and the residual `x + h` ride in its epilogue;
+* activations never leave one layout: a zero-haloed channels-last grid `[T, H + 2, W + 2, C]` bf16 (the halo = the spatial
+  padding; the causal padding frames are not stored: the convolution addresses them with negative row coordinates, which
+  TMA fills with zeros). Every convolution of the network — 3x3x3 causal, (3,1,1) temporal, per-frame 3x3, 1x1 — is one
+  launch of the tap-GEMM tcgen05 kernel (`mmpl_conv3d_cl`) reading that grid in place; bias and the residual `x + h` ride
+  in its epilogue, and every kernel writes the halo of its output as zeros, so no buffer is ever cleared;
 * one pass per layer over ALL frames instead of the reference's per-frame / per-chunk passes with carried frames
   (`feat_cache`): the carried frames are exactly the causal left context. The two places where the chunked schedule
   is not a plain causal convolution are kept as the reference has them: the temporal up-sampler skips frame 0 and
@@ -30,8 +31,6 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-
-LEAD = 2  # leading zero frames of every grid = temporal padding of a 3-tap causal convolution
 
 # utils/wan_wrapper.py:52-63
 LATENT_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
@@ -183,7 +182,7 @@ class WanVAEWrapper(torch.nn.Module):
     # ----------------------------------------------------------------------------------------------- primitives
     def _conv(self, name: str, grid: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         return ops.conv3d_causal_cl(grid, self._w[name + ".weight"], self._w.get(name + ".bias"), self._kernel[name],
-                                    lead=LEAD, residual=residual)
+                                    history=0, residual=residual)
 
     def _res_block(self, p: str, x: torch.Tensor) -> torch.Tensor:
         """ResidualBlock.forward (vae.py:189-213): shortcut(x) + conv(silu(norm(conv(silu(norm(x))))))."""
@@ -199,7 +198,7 @@ class WanVAEWrapper(torch.nn.Module):
         n = (hp - 2) * (wp - 2)
         xn = ops.vae_norm_act(x, self._w[p + ".norm.gamma"], silu=False)
         out = torch.zeros_like(x)
-        for f in range(LEAD, frames):
+        for f in range(frames):
             rows = xn[f, 1:-1, 1:-1].reshape(n, c)                      # compact copy of the interior
             ident = x[f, 1:-1, 1:-1].reshape(n, c)
             qkv = ops.linear(rows, self._w[p + ".to_qkv.weight"], self._w[p + ".to_qkv.bias"])
@@ -214,17 +213,15 @@ class WanVAEWrapper(torch.nn.Module):
 
     def _up(self, p: str, x: torch.Tensor, temporal: bool) -> torch.Tensor:
         """Resample 'upsample2d' / 'upsample3d' (vae.py:98-136) over the whole frame axis."""
-        frames, hp, wp, c = x.shape
-        t = frames - LEAD
+        t, hp, wp, c = x.shape
         if temporal and t > 1:
-            # frames 1.. through the (3,1,1) convolution with zero history in front of frame 1, two frames out per frame in
-            rest = torch.zeros((LEAD + t - 1, hp, wp, c), dtype=x.dtype, device=x.device)
-            rest[LEAD:] = x[LEAD + 1:]
-            y = self._conv(p + ".time_conv", rest)                      # [.., 2c]
-            wide = torch.zeros((LEAD + 1 + 2 * (t - 1), hp, wp, c), dtype=x.dtype, device=x.device)
-            wide[LEAD] = x[LEAD]
-            wide[LEAD + 1::2] = y[LEAD:, :, :, :c]
-            wide[LEAD + 2::2] = y[LEAD:, :, :, c:]
+            # frames 1.. through the (3,1,1) convolution with zero history in front of frame 1 (a view: the zeros are
+            # implicit), two frames out per frame in, interleaved behind frame 0
+            y = self._conv(p + ".time_conv", x[1:])                     # [t - 1, .., 2c]
+            wide = torch.empty((1 + 2 * (t - 1), hp, wp, c), dtype=x.dtype, device=x.device)
+            wide[0] = x[0]
+            wide[1::2] = y[..., :c]
+            wide[2::2] = y[..., c:]
             x = wide
         x = ops.vae_upsample2x(x)
         return self._conv(p + ".resample.1", x)
@@ -232,16 +229,12 @@ class WanVAEWrapper(torch.nn.Module):
     def _down(self, p: str, x: torch.Tensor, temporal: bool) -> torch.Tensor:
         """Resample 'downsample2d' / 'downsample3d' (vae.py:133-155) over the whole frame axis."""
         x = ops.vae_pick_odd(self._conv(p + ".resample.1", x))
-        frames = x.shape[0]
-        t = frames - LEAD
+        t = x.shape[0]
         if temporal and t > 1:
-            # stride-2 windows (0,1,2), (2,3,4), ... of the un-padded sequence = the causal convolution at frames 2, 4, ...
+            # stride-2 windows (0,1,2), (2,3,4), ... of the un-padded sequence = the causal convolution at frames 2, 4, ...;
+            # frame 0 passes through
             y = self._conv(p + ".time_conv", x)
-            keep = [LEAD] + list(range(LEAD + 2, frames, 2))
-            out = torch.zeros((LEAD + len(keep),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-            out[LEAD] = x[LEAD]
-            out[LEAD + 1:] = y[keep[1:]]
-            x = out
+            x = torch.cat([x[:1], y[2::2]], dim=0)
         return x
 
     def _run(self, prog, x):
@@ -262,24 +255,24 @@ class WanVAEWrapper(torch.nn.Module):
         """WanVAE_.decode (vae.py:530-552). z [z_dim, T, h, w] bf16 -> [3, 1 + 4(T-1), 8h, 8w] bf16."""
         mean = self.mean.to(device=z.device, dtype=z.dtype).view(-1, 1, 1, 1)
         inv_std = (1.0 / self.std.to(device=z.device, dtype=z.dtype)).view(-1, 1, 1, 1)
-        x = ops.to_haloed(z / inv_std + mean, lead=LEAD)
+        x = ops.to_haloed(z / inv_std + mean)
         x = self._conv("conv2", x)
         x = self._conv("decoder.conv1", x)
         x = self._run(self._dec, x)
         x = ops.vae_norm_act(x, self._w["decoder.head.0.gamma"], silu=True)
         x = self._conv("decoder.head.2", x)
-        return ops.from_haloed(x, LEAD, 3)
+        return ops.from_haloed(x, 3)
 
     @torch.no_grad()
     def _encode_one(self, pixels: torch.Tensor) -> torch.Tensor:
         """WanVAE_.encode (vae.py:501-528). pixels [3, 1 + 4k, H, W] bf16 -> mu [z_dim, 1 + k, H/8, W/8] bf16."""
-        x = ops.to_haloed(pixels, lead=LEAD)
+        x = ops.to_haloed(pixels)
         x = self._conv("encoder.conv1", x)
         x = self._run(self._enc, x)
         x = ops.vae_norm_act(x, self._w["encoder.head.0.gamma"], silu=True)
         x = self._conv("encoder.head.2", x)
         x = self._conv("conv1", x)
-        mu = ops.from_haloed(x, LEAD, self.z_dim)                       # .chunk(2, dim=1)[0]
+        mu = ops.from_haloed(x, self.z_dim)                       # .chunk(2, dim=1)[0]
         mean = self.mean.to(device=mu.device, dtype=mu.dtype).view(-1, 1, 1, 1)
         inv_std = (1.0 / self.std.to(device=mu.device, dtype=mu.dtype)).view(-1, 1, 1, 1)
         return (mu - mean) * inv_std

@@ -84,7 +84,7 @@ def test_no_cpu_fallback():
         _lib.check(rc)
     # the VAE segment-connect entry points refuse as well (arch check before any pointer is touched)
     fake = C.c_void_p(0x1000)
-    assert lib.mmpl_conv3d_cl(fake, fake, None, fake, None, 1, 4, 4, 8, 8, 3, 3, 3, None) == -2
+    assert lib.mmpl_conv3d_cl(fake, fake, None, fake, None, 1, 4, 4, 8, 8, 3, 3, 3, 0, None) == -2
     assert lib.mmpl_vae_norm_act(fake, fake, 16, 8, fake, 1, None) == -2
     assert lib.mmpl_vae_upsample2x(fake, fake, 1, 4, 4, 8, None) == -2
     assert lib.mmpl_vae_pick_odd(fake, fake, 1, 4, 4, 8, None) == -2

@@ -35,6 +35,9 @@ CASES = [
     (192, 96, (1, 3, 3), 3, 16, 24, 0, False),    # per-frame Conv2d 3x3 of the up-sampler
     (96, 3, (3, 3, 3), 2, 16, 24, 0, False),      # decoder head: 3 output channels in an 8-channel layout
     (3, 96, (3, 3, 3), 2, 16, 24, 0, False),      # encoder conv1: 3 input channels in an 8-channel layout
+    (96, 192, (3, 3, 3), 3, 30, 52, 1, True),     # 96-wide tiles over two N tiles, one carried frame, row-packed K = 5 blocks
+    (192, 192, (3, 3, 3), 2, 17, 23, 0, False),   # odd grid sizes: M tail, halo rows inside every tile
+    (96, 96, (1, 3, 3), 5, 60, 104, 0, False),    # many M tiles, the first / last rows of the tensor map in play
 ]
 
 
@@ -56,22 +59,20 @@ def test_conv3d_tap_gemm(cin, cout, kernel, T, H, W, hist, with_res):
         ref = (ref + res.unsqueeze(0)).to(torch.bfloat16)    # ResidualBlock: x + h in bf16 (vae.py:213)
     ref = ref[0]
 
-    lead = 2
-    grid = ops.to_haloed(x[:, hist:], lead=lead)
-    if hist:
-        grid[lead - hist:lead] = ops.to_haloed(x[:, :hist], lead=0)
-    res_grid = ops.to_haloed(res, lead=lead) if with_res else None
-    out = ops.conv3d_causal_cl(grid, ops.pack_conv_weight(w), b, kernel, lead=lead, residual=res_grid)
+    grid = ops.to_haloed(x)                                   # [hist + T, H + 2, W + 2, C8]: carried frames in front
+    res_grid = ops.to_haloed(res) if with_res else None
+    # the output buffer starts as garbage: the kernel must write every position, the halo as zeros
+    out = torch.full((T, H + 2, W + 2, -(-cout // 8) * 8), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.conv3d_causal_cl(grid, ops.pack_conv_weight(w), b, kernel, history=hist, residual=res_grid, out=out)
     torch.cuda.synchronize()
-    _check(f"conv {cin}->{cout} k{kernel} T{T} {H}x{W} hist{hist}", ops.from_haloed(out, lead, cout), ref)
-    # the halo and the leading frames are never written
-    assert float(out[:lead].abs().max()) == 0 and float(out[:, 0].abs().max()) == 0 and float(out[:, -1].abs().max()) == 0
+    _check(f"conv {cin}->{cout} k{kernel} T{T} {H}x{W} hist{hist}", ops.from_haloed(out, cout), ref)
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, -1].abs().max()) == 0
     assert float(out[:, :, 0].abs().max()) == 0 and float(out[:, :, -1].abs().max()) == 0
     assert float(out[..., cout:].abs().max() if out.shape[-1] > cout else 0.0) == 0
 
 
 def test_conv3d_chain_matches_whole_sequence():
-    """Two stacked convolutions on the haloed grid without leaving the layout (the halo written by nobody stays zero, so
+    """Two stacked convolutions on the haloed grid without leaving the layout (each writes its output's halo as zeros, so
     the second convolution sees correct spatial padding): equals the oracle's whole-sequence causal convolutions."""
     from mmpl_b200 import ops
     x = _rand(96, 4, 12, 20, seed=5)
@@ -113,14 +114,16 @@ def test_vae_norm_act(C, silu):
 def test_vae_upsample_and_pick():
     from mmpl_b200 import ops
     x = _rand(24, 3, 6, 10, seed=13)
-    g = ops.to_haloed(x, lead=1)
+    g = ops.to_haloed(x)
     up = ops.vae_upsample2x(g)
     want = torch.nn.functional.interpolate(x.float().permute(1, 0, 2, 3), scale_factor=(2.0, 2.0), mode="nearest")
-    assert torch.equal(ops.from_haloed(up, 1).float(), want.permute(1, 0, 2, 3))
-    assert float(up[:1].abs().max()) == 0 and float(up[:, 0].abs().max()) == 0 and float(up[:, :, -1].abs().max()) == 0
+    assert torch.equal(ops.from_haloed(up).float(), want.permute(1, 0, 2, 3))
+    assert float(up[:, 0].abs().max()) == 0 and float(up[:, -1].abs().max()) == 0
+    assert float(up[:, :, 0].abs().max()) == 0 and float(up[:, :, -1].abs().max()) == 0      # halo written as zeros
     pick = ops.vae_pick_odd(g)
-    assert torch.equal(ops.from_haloed(pick, 1), x[:, :, 1::2, 1::2])
-    assert float(pick[:, 0].abs().max()) == 0 and float(pick[:, :, 0].abs().max()) == 0
+    assert torch.equal(ops.from_haloed(pick), x[:, :, 1::2, 1::2])
+    assert float(pick[:, 0].abs().max()) == 0 and float(pick[:, -1].abs().max()) == 0
+    assert float(pick[:, :, 0].abs().max()) == 0 and float(pick[:, :, -1].abs().max()) == 0
 
 
 def test_strided_conv_equals_same_conv_plus_pick():

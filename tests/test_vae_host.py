@@ -24,35 +24,41 @@ def _r(x):  # one bf16 rounding
 
 
 # ---------------------------------------------------------------------------------- kernel contracts, emulated
-def emu_conv3d_causal_cl(grid, w_packed, bias, kernel, lead=2, residual=None, out=None):
-    """mmpl_conv3d_cl: every grid position is a GEMM row, a tap is a row shift (zero outside the tensor), interior stores."""
+def emu_conv3d_causal_cl(grid, w_packed, bias, kernel, history=0, residual=None, out=None):
+    """mmpl_conv3d_cl (include/mmpl_b200.h): every grid position is a GEMM row; a K span is a row shift of the grid read as
+    one contiguous run (Cin elements for KW = 1, the three dw taps = 3*Cin elements starting one row earlier for KW = 3),
+    zeros outside the tensor; the causal padding frames that are not stored (`history` < KT-1) are rows with negative
+    coordinates; interior positions get the result, halo positions zeros."""
     kt, kh, kw = kernel
     frames, hp, wp, cin = grid.shape
-    t, cout = frames - lead, w_packed.shape[0]
-    a = grid.reshape(-1, cin).float()
-    base, rows_in, m = (lead - (kt - 1)) * hp * wp, (t + kt - 1) * hp * wp, t * hp * wp
+    t, cout = frames - history, w_packed.shape[0]
+    flat = grid.reshape(-1).float()
+    rows_in, m = frames * hp * wp, t * hp * wp
+    span = 3 * cin if kw == 3 else cin
     acc = torch.zeros(m, cout)
     r = torch.arange(m)
     i = 0
     for dt in range(kt):
         for dh in range(kh):
-            for dw in range(kw):
-                idx = r + (dt * hp + (dh - kh // 2)) * wp + (dw - kw // 2)
-                ok = (idx >= 0) & (idx < rows_in)
-                rows = torch.zeros(m, cin)
-                rows[ok] = a[base + idx[ok]]
-                acc += rows @ w_packed[:, i, :cin].float().T
+            frame_row = ((dt - (kt - 1) + history) * hp + (dh - kh // 2)) * wp
+            for dw in ([None] if kw == 3 else range(kw)):
+                first = r + frame_row + (-1 if kw == 3 else dw - kw // 2)          # first grid row of the span
+                limit = rows_in - 2 if kw == 3 else rows_in                          # rows the tensor map covers
+                ok = (first >= 0) & (first < limit)
+                a = torch.zeros(m, span)
+                gather = first[ok, None] * cin + torch.arange(span)[None, :]
+                a[ok] = flat[gather]
+                acc += a @ w_packed[:, i, :span].float().T
                 i += 1
     if bias is not None:
         b = bias.float().reshape(-1)
         acc[:, :b.numel()] += b
     y = _r(acc)
     if residual is not None:
-        y = _r(residual.reshape(-1, cout)[lead * hp * wp:].float() + y)
-    res = torch.zeros(frames, hp, wp, cout, dtype=BF)
+        y = _r(residual.reshape(-1, cout).float() + y)
     interior = ((r % wp) >= 1) & ((r % wp) < wp - 1) & (((r // wp) % hp) >= 1) & (((r // wp) % hp) < hp - 1)
-    res.reshape(-1, cout)[lead * hp * wp + r[interior]] = y[interior].to(BF)
-    return res
+    y[~interior] = 0
+    return y.to(BF).reshape(t, hp, wp, cout)
 
 
 def emu_vae_norm_act(grid, gamma, silu=True, out=None):
