@@ -18,9 +18,15 @@ import sys
 import time
 import types
 
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
+# stdout carries JSON lines only: fd 1 is pointed at stderr for libraries (NCCL's version banner), emit() writes to the saved fd
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(record):
+    os.write(_STDOUT_FD, (json.dumps(record) + "\n").encode())
+
 
 import torch
 import torch.distributed as dist
@@ -79,7 +85,9 @@ def main():
         nbytes = broadcast_weights(model, src=0)
         torch.cuda.synchronize()
         if rank == 0:
-            print(f"broadcast_weights: {nbytes / 1e9:.1f} GB in {time.perf_counter() - tb:.2f} s", file=sys.stderr)
+            dt = time.perf_counter() - tb
+            emit({"what": "broadcast_weights: rank 0's parameters to every rank over NCCL (one checkpoint load per box)",
+                  "n_gpus": world, "gigabytes": nbytes / 1e9, "seconds": dt, "gb_per_s": nbytes / 1e9 / dt})
     gen = WanFPSWrapper(model=model, timestep_shift=5.0)
     build_s = time.perf_counter() - t0
     chain, chain_group, chain_ranks = (0, None, list(range(world)))
@@ -172,13 +180,13 @@ def main():
             flags = [None] * world
             dist.all_gather_object(flags, finite)
         if rank == 0:
-            print(json.dumps({
+            emit({
                 "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
                 "value": a.videos * a.segments * 21 / (ms.item() / 1e3), "ms_total": ms.item(),
                 "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'}: {a.videos} queued videos x {a.segments} segments x 21 latent "
                                        f"frames 60x104 through the resident scheduler, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
                            "parallelism": f"chains chosen per round, {lanes} lane(s) per segment, min {a.min_slots} slot(s) per chain"},
-                "finite": all(flags), "history": svc.history, "connect": connect_name, "model_build_s": build_s}))
+                "finite": all(flags), "history": svc.history, "connect": connect_name, "model_build_s": build_s})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -214,14 +222,14 @@ def main():
             gathered = [None] * world
             dist.all_gather_object(gathered, info)
         if rank == 0:
-            print(json.dumps({
+            emit({
                 "metric": "denoised_latent_frames_per_s", "unit": "latent frames/s", "n_gpus": world,
                 "value": a.chains * nseg * 21 / (ms.item() / 1e3), "ms_total": ms.item(), "wall_s_incl_barrier": total_wall,
                 "config": {"workload": f"Wan2.1-{a.model} MMPL {'I2V' if a.i2v else 'T2V'} segment-parallel, {a.chains} chain(s) x {nseg} segments x 21 latent frames 60x104, "
                                        f"stages {'[1,1,7,6,6]' if a.i2v else '[2,7,6,6]'}, {a.sampling_steps} UniPC steps x CFG, {dims['num_layers']} blocks",
                            "parallelism": ((f"{a.chains} independent chains, each " if a.chains > 1 else "") + f"segment-parallel x{cworld // lanes} slots" + (" x 2 CFG lanes (flow all-gather per step)" if a.cfg_pair else "") +
                                            ", anchors over NCCL send/recv")},
-                "connect": connect_name, "model_build_s": build_s, "ranks": gathered}))
+                "connect": connect_name, "model_build_s": build_s, "ranks": gathered})
 
     # --sweep: several chain lengths against one model build (BASELINE config 5: 5-60 s videos)
     for nseg in ([int(x) for x in a.sweep.split(',')] if a.sweep else [a.segments]):
