@@ -238,7 +238,7 @@ def _bcast_worker(rank, world, port, q):
         torch.manual_seed(100 + rank)   # every rank starts from different weights
         m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Linear(32, 8)).to(torch.bfloat16)
         m.register_buffer("table", torch.randn(5, 3, dtype=torch.float64))
-        n = broadcast_weights(m, src=0, bucket_bytes=600)   # small buckets: several collectives, mixed dtypes
+        n = broadcast_weights(m, src=0, bucket_bytes=600, direct_bytes=1024)   # small buckets + one tensor sent in place, mixed dtypes
         # raw bytes travel through the queue by value (torch tensors would go through shared-memory handles that die with
         # this process: a race with the parent's q.get)
         q.put((rank, n, {k: (str(v.dtype), tuple(v.shape), v.contiguous().view(torch.uint8).numpy().tobytes())

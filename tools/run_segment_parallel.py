@@ -80,7 +80,9 @@ def main():
     model = model.to(torch.bfloat16).eval().requires_grad_(False)
     if a.broadcast_weights and world > 1:
         from mmpl_b200.segment_parallel import broadcast_weights
+        dist.broadcast(torch.zeros(8, device=dev), src=0)   # communicator set-up is not part of the transfer
         torch.cuda.synchronize()
+        dist.barrier()
         tb = time.perf_counter()
         nbytes = broadcast_weights(model, src=0)
         torch.cuda.synchronize()
