@@ -80,6 +80,11 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return __fdividef(x, 1.0f + e);
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ void round2f(float& a, float& b) {  // both to bf16 and back: one packed conversion + two integer ops
+  const uint32_t p = pack_bf16x2(a, b);
+  a = bf16_lo(p);
+  b = bf16_hi(p);
+}
 
 // Epilogue of one accumulator row: `taddr` addresses this warp's 32 TMEM lanes at the tile's first column; the
 // thread owns output row `row`, columns [col_base, col_base + BN). Rounds to bf16 where the reference does.
@@ -182,8 +187,11 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsOf<CONV>::typ
           const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gv);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]));
-            float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]));
+            // roundings in pairs: cvt.rn.bf16x2.f32 issues at 2 clk per warp instruction, the scalar conversion at 8
+            // (profiles/r01_microbench_pipes.txt), and an unfused Linear needs none before the pack below
+            float y0 = __uint_as_float(acc[g * 8 + 2 * j]) + bf16_lo(bw[j]);
+            float y1 = __uint_as_float(acc[g * 8 + 2 * j + 1]) + bf16_hi(bw[j]);
+            if (EPI != MMPL_EPI_BIAS) round2f(y0, y1);
             if (EPI == MMPL_EPI_BIAS_GELU) {
               y0 = gelu_tanh_f(y0);
               y1 = gelu_tanh_f(y1);
@@ -194,8 +202,11 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsOf<CONV>::typ
               y0 = bf16_lo(rw[j]) + y0;
               y1 = bf16_hi(rw[j]) + y1;
             } else if (EPI == MMPL_EPI_BIAS_GATE_RES) {
-              y0 = bf16_lo(rw[j]) + bf16_round(y0 * bf16_lo(gw[j]));
-              y1 = bf16_hi(rw[j]) + bf16_round(y1 * bf16_hi(gw[j]));
+              y0 *= bf16_lo(gw[j]);
+              y1 *= bf16_hi(gw[j]);
+              round2f(y0, y1);
+              y0 += bf16_lo(rw[j]);
+              y1 += bf16_hi(rw[j]);
             }
             ow[gg * 4 + j] = pack_bf16x2(y0, y1);
           }
