@@ -525,7 +525,7 @@ def main():
     ap.add_argument("--cpu-sample", default="same", choices=["same", "cfg2_chunk0", "cfg1", "tiny"],
                     help="what the CPU arm times: `same` = the whole workload for --impl reference and its first chunk for the "
                          "in-line cpu_baseline")
-    ap.add_argument("--cpu-budget", type=float, default=600.0, help="--impl reference: stop adding steps beyond this many seconds")
+    ap.add_argument("--cpu-budget", type=float, default=500.0, help="--impl reference: stop adding steps beyond this many seconds")
     ap.add_argument("--no-chain", action="store_true", help="skip the MMPL segment-parallel `chain` record")
     ap.add_argument("--chain-steps", type=int, default=50, help="UniPC steps of the chain record (the reference's 50)")
     ap.add_argument("--chain-layers", type=int, default=0, help="override the 14B model's 40 blocks (quick checks only)")
