@@ -5,8 +5,9 @@ re-encoded to 2 latents. CUDA events on the launching stream, warm-up first; see
 
     python tools/bench_vae_connect.py [--iters 5] [--warmup 2] [--latent-h 60 --latent-w 104] [--i2v]
 
-Prints one JSON line: ms per connect, algorithmic TFLOP (2 x positions x taps x Cin x Cout over every convolution + the
+Prints JSON lines: first the connect - ms per connect, algorithmic TFLOP (2 x positions x taps x Cin x Cout over every convolution + the
 middle attention) and the fraction of the measured sustained bf16 peak (MEASURED_PEAKS.json), plus the per-call launch count.
+Then the final 21 -> 81 frame decode of a segment and the i2v image encode (skip with --skip-extras).
 Run under `ncu --set full -k regex:gemm_bf16_kernel` for the tap-GEMM capture."""
 import argparse
 import ctypes as C
@@ -74,6 +75,7 @@ def main():
     ap.add_argument("--latent-h", type=int, default=60)
     ap.add_argument("--latent-w", type=int, default=104)
     ap.add_argument("--i2v", action="store_true", help="3 anchors (frames 0, 19, 20) instead of the t2v payload of 8")
+    ap.add_argument("--skip-extras", action="store_true", help="only the connect (no final decode / image encode timing)")
     a = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: the mmpl_b200 path has no CPU fallback")
@@ -104,10 +106,39 @@ def main():
     except Exception:
         pass
     tf = flops / (ms * 1e-3) / 1e12
-    print(json.dumps({"what": "vae segment connect", "ms": ms, "algorithmic_tflop": flops / 1e12, "tflops": tf, "peak_tflops": peak,
+    record = lambda d: print(json.dumps(d), flush=True)  # noqa: E731
+    record({"what": "vae segment connect", "ms": ms, "algorithmic_tflop": flops / 1e12, "tflops": tf, "peak_tflops": peak,
                       "frac_of_sustained_bf16_peak": tf / peak, "gpu_launches_per_connect": launches,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "finite": bool(torch.isfinite(out.float()).all()),
-                      "geometry": f"latent {a.latent_h}x{a.latent_w}, 4 latent -> 13 pixel frames decoded, 5 pixel frames encoded"}))
+                      "geometry": f"latent {a.latent_h}x{a.latent_w}, 4 latent -> 13 pixel frames decoded, 5 pixel frames encoded"})
+    if a.skip_extras:
+        return
+
+    def timed(fn, iters=2):
+        fn()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(iters):
+            y = fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / iters, y
+
+    # the decode that ends a segment (pipeline/casual_fps_inference.py:445: vae.decode_to_pixel(output), 21 latent -> 81 pixel
+    # frames at 480x832) and the i2v image encode (MMPL_i2v/Wan_fps_inference_parallel_4gpu_20s.py:190-194: one frame)
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(1, 21, 16, a.latent_h, a.latent_w, generator=g).to(torch.bfloat16).to(dev)
+    torch.cuda.reset_peak_memory_stats()
+    ms_dec, video = timed(lambda: vae.decode_to_pixel(lat))
+    record({"what": "final decode of one segment: 21 latent frames -> 81 pixel frames", "ms": ms_dec, "shape": list(video.shape),
+            "finite": bool(torch.isfinite(video).all()), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+            "pixel_frames_per_s": video.shape[1] / (ms_dec / 1e3)})
+    del video
+    image = (torch.rand(1, 3, 1, 8 * a.latent_h, 8 * a.latent_w, generator=g) * 2 - 1).to(torch.bfloat16).to(dev)
+    ms_enc, z = timed(lambda: vae.encode_to_latent(image), iters=5)
+    record({"what": "i2v image encode: 1 pixel frame -> 1 latent frame", "ms": ms_enc, "shape": list(z.shape),
+            "finite": bool(torch.isfinite(z).all())})
 
 
 if __name__ == "__main__":

@@ -238,6 +238,28 @@ class ChainBench:
             "segment_times_rank0": gathered[0]["segment_times"],
         }
 
+    def time_final_decode(self) -> Optional[dict]:
+        """The decode that ends a segment in the reference (pipeline/casual_fps_inference.py:445: all 21 latent frames -> 81
+        pixel frames at 480x832) and the i2v image encode, on this rank's GPU. Outside the denoise bracket the metric is
+        defined on, so reported next to the chain numbers, not inside them."""
+        if self.vae is None:
+            return None
+        lat = torch.randn(1, FRAMES, 16, LAT_H, LAT_W, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).to(self.device)
+        image = (torch.rand(1, 3, 1, 8 * LAT_H, 8 * LAT_W, generator=torch.Generator().manual_seed(4)) * 2 - 1).to(torch.bfloat16).to(self.device)
+        out = {}
+        for name, fn in (("final_decode_ms", lambda: self.vae.decode_to_pixel(lat)), ("image_encode_ms", lambda: self.vae.encode_to_latent(image))):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = self._mark(), None
+            y = fn()
+            e1 = self._mark()
+            torch.cuda.synchronize()
+            out[name] = round(e0.elapsed_time(e1), 2)
+            out[name.replace("_ms", "_finite")] = bool(torch.isfinite(y).all())
+            del y
+        out["note"] = "21 latent -> 81 pixel frames at 480x832, and one image frame -> one latent; outside the denoise bracket"
+        return out
+
     @staticmethod
     def _mark():
         ev = torch.cuda.Event(enable_timing=True)
