@@ -293,6 +293,8 @@ def run_chain(args, rank, world, device, deadline):
     records, skipped = [], []
     est_forward_s = 0.30 * cb.dims["num_layers"] / 40   # prior: one 14B forward of ~6 frames on a B200; replaced by measurements
     for v in cb.variants():
+        if args.chain_layouts and str(v["chains"]) not in args.chain_layouts.split(","):
+            continue
         segs = 2 if v["slots"] == 1 else (3 * v["slots"] if v["chains"] > 1 else 4)
         # predicted wall time: segments run back to back on a slot; a chain emits one segment per anchor stage (~0.37 T_seg)
         steps = args.chain_steps
@@ -531,6 +533,7 @@ def main():
     ap.add_argument("--no-chain", action="store_true", help="skip the MMPL segment-parallel `chain` record")
     ap.add_argument("--chain-steps", type=int, default=50, help="UniPC steps of the chain record (the reference's 50)")
     ap.add_argument("--chain-layers", type=int, default=0, help="override the 14B model's 40 blocks (quick checks only)")
+    ap.add_argument("--chain-layouts", default="", help="comma-separated chain counts to measure (default: every layout of the box)")
     ap.add_argument("--chain-no-vae", action="store_true", help="pass-through connect instead of the VAE (labelled in the record)")
     ap.add_argument("--time-budget", type=float, default=780.0,
                     help="wall seconds the whole run may take: chain layouts that would not fit run with fewer UniPC steps "
