@@ -56,33 +56,42 @@ __device__ __forceinline__ double widen(float f) {
 //   affine    (norm3, causal_model.py:314; model.py:89-99): out = bf16( LN(x) * w + b )
 // NCH = D / 256 (16-byte chunks per lane).
 template <int NCH, bool AFFINE>
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
+__global__ void __launch_bounds__(kRowsPerBlock * 32, NCH <= 8 ? 4 : 1)  // D <= 2048: 64 registers, S = 4680 rows in one wave
 ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ldo,
           int S, float eps, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
           int64_t mod_stride, int rows_per_frame) {
   pdl_wait();  // PDL: the previous kernel in the stream has completed, its writes are visible
   pdl_launch_dependents();
   constexpr int D = NCH * 256;
-  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= S) return;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
-  uint4 v[NCH];
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) v[i] = xr[lane + 32 * i];
-  // the modulation / affine vectors are fetched together with the row, so their latency is paid once
-  const int frame = row / rows_per_frame;
-  const uint4* a_ptr = reinterpret_cast<const uint4*>(AFFINE ? scale : scale + static_cast<int64_t>(frame) * mod_stride);
-  const uint4* b_ptr = reinterpret_cast<const uint4*>(AFFINE ? shift : shift + static_cast<int64_t>(frame) * mod_stride);
-  constexpr bool kPrefetch = NCH <= 8;
-  uint4 av[kPrefetch ? NCH : 1], bv[kPrefetch ? NCH : 1];
-  if (kPrefetch) {
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      av[i] = __ldg(a_ptr + lane + 32 * i);
-      bv[i] = __ldg(b_ptr + lane + 32 * i);
+  // The modulation (shift, scale of the CTA's frame) or affine (weight, bias) vectors are the same for every row of the
+  // CTA - a frame is hundreds of rows, a CTA eight - so they are staged once per CTA in shared memory instead of being
+  // held per warp in 2 x NCH x 4 registers: that was what kept the kernel at 2-3 CTAs per SM and two waves at S = 4680.
+  // A row of another frame than the CTA's first (only when rows_per_frame is not a multiple of 8) reads them from global.
+  __shared__ uint4 s_a[NCH * 32], s_b[NCH * 32];
+  const int row0 = blockIdx.x * kRowsPerBlock;
+  const int frame0 = row0 / rows_per_frame;
+  {
+    const uint4* a0 = reinterpret_cast<const uint4*>(AFFINE ? scale : scale + static_cast<int64_t>(frame0) * mod_stride);
+    const uint4* b0 = reinterpret_cast<const uint4*>(AFFINE ? shift : shift + static_cast<int64_t>(frame0) * mod_stride);
+    for (int i = threadIdx.x; i < NCH * 32; i += kRowsPerBlock * 32) {
+      s_a[i] = __ldg(a0 + i);
+      s_b[i] = __ldg(b0 + i);
     }
   }
+  const int row = row0 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  uint4 v[NCH];
+  if (row < S) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) v[i] = xr[lane + 32 * i];
+  }
+  __syncthreads();
+  if (row >= S) return;
+  const int frame = row / rows_per_frame;
+  const bool staged = AFFINE || frame == frame0;
+  const uint4* a_ptr = reinterpret_cast<const uint4*>(AFFINE ? scale : scale + static_cast<int64_t>(frame) * mod_stride);
+  const uint4* b_ptr = reinterpret_cast<const uint4*>(AFFINE ? shift : shift + static_cast<int64_t>(frame) * mod_stride);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
@@ -109,8 +118,8 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
   for (int i = 0; i < NCH; ++i) {
     float f[8], a[8], b[8];
     unpack8(v[i], f);
-    unpack8(kPrefetch ? av[i] : __ldg(a_ptr + lane + 32 * i), a);
-    unpack8(kPrefetch ? bv[i] : __ldg(b_ptr + lane + 32 * i), b);
+    unpack8(staged ? s_a[lane + 32 * i] : __ldg(a_ptr + lane + 32 * i), a);
+    unpack8(staged ? s_b[lane + 32 * i] : __ldg(b_ptr + lane + 32 * i), b);
     if (AFFINE) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(__fmul_rn((f[j] - mean) * rstd, a[j]), b[j]);
