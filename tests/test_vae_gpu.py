@@ -196,3 +196,42 @@ def test_connect_at_reference_resolution_properties():
     cos = torch.nn.functional.cosine_similarity(full.flatten(), head.flatten(), dim=0).item()
     print(f"full-size decode prefix: exact={bool(torch.equal(full, head))} max_abs={float((full - head).abs().max()):.4g} cos={cos:.6f}")
     assert full.shape == head.shape == (1, 5, 3, 480, 832) and cos >= 0.9999
+
+
+def test_pipeline_ends_in_the_native_vae_decode():
+    """The last statement of the reference pipelines, `video = vae.decode_to_pixel(output); (video * 0.5 + 0.5).clamp(0, 1)`
+    (pipeline/causal_inference.py:255-256, casual_fps_inference.py:445-446), with `mmpl_b200.vae.WanVAEWrapper` injected as the
+    pipeline's `vae`: the few-step pipeline on the CUDA model returns the video of its own latents, checked against the VAE
+    oracle's decode of those latents (6 latent frames -> 21 pixel frames at 64x96)."""
+    import types
+    from mmpl_b200.causal_model import CausalWanModel
+    from mmpl_b200.pipeline import CausalInferencePipeline
+    from mmpl_b200.vae import WanVAEWrapper
+    from mmpl_b200.wan_wrapper import WanDiffusionWrapper
+    from oracle import causal_wan_oracle as O
+    cfg = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
+    m = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
+                       num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+    m.load_state_dict(O.make_weights(cfg, 2))
+    gen = WanDiffusionWrapper(model=m.to(DEV, torch.bfloat16).eval(), timestep_shift=5.0)
+    vcfg = V.VaeConfig()
+    W = V.make_weights(vcfg, 0, torch.bfloat16)
+    vae = WanVAEWrapper()
+    vae.load_vae_state_dict(W, device=DEV)
+    prompt = torch.randn(1, cfg.text_len, cfg.text_dim, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(DEV)
+
+    class Text(torch.nn.Module):
+        def forward(self, text_prompts):
+            return {"prompt_embeds": prompt}
+
+    args = types.SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True, independent_first_frame=False,
+                                 context_noise=0, num_frame_per_block=3, model_kwargs={})
+    pipe = CausalInferencePipeline(args, torch.device(DEV), generator=gen, text_encoder=Text(), vae=vae)
+    noise = torch.randn(1, 6, 16, 8, 12, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).to(DEV)
+    video, latents = pipe.inference(noise=noise, text_prompts=["p"], return_latents=True)
+    assert video.shape == (1, 21, 3, 64, 96) and float(video.min()) >= 0 and float(video.max()) <= 1
+    want = (V.decode_to_pixel(W, vcfg, latents.cpu()) * 0.5 + 0.5).clamp(0, 1)
+    err = float((video.float().cpu() - want.float()).abs().max())
+    cos = torch.nn.functional.cosine_similarity(video.float().cpu().flatten(), want.float().flatten(), dim=0).item()
+    print(f"pipeline video vs oracle decode of its latents: max_abs={err:.4g} cos={cos:.6f}")
+    assert err <= 0.04 and cos >= 0.9995     # half of the decode tolerance: the video is decode * 0.5 + 0.5
