@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MMPL_ABI_VERSION 3
+#define MMPL_ABI_VERSION 4
 
 enum {
   MMPL_OK = 0,
@@ -237,6 +237,14 @@ int mmpl_bind_weight(mmpl_ctx* ctx, const char* name, const void* ptr, int64_t n
 int mmpl_bind_rope_table(mmpl_ctx* ctx, const void* table /* device double [1024][64][2] */);
 /* Number of kernels the context launched since the last call with reset != 0. */
 int64_t mmpl_launch_count(mmpl_ctx* ctx, int reset);
+/* Changes whenever the library reallocates one of its process-level device workspaces (attention partials, merge
+ * counters, stream-K slots): a CUDA graph captured from mmpl_forward is valid only while this value is the one seen
+ * at capture. */
+int64_t mmpl_workspace_generation(void);
+/* Adds n (may be negative) to the context's and the process's launch counters and returns the context's: a host that
+ * captures a forward's launch sequence in a CUDA graph credits the captured count for every replay, so that the counters
+ * keep meaning "kernels of this library that ran". */
+int64_t mmpl_launch_credit(mmpl_ctx* ctx, int64_t n);
 /* Kernels launched through any entry point of this library in this process (bench.py "gpu_launches"). */
 int64_t mmpl_total_launches(int reset);
 
@@ -246,6 +254,7 @@ int64_t mmpl_total_launches(int reset);
  * algorithmic work (FLOPs for categories 0-2, bytes for 3) and the launch count. */
 enum { MMPL_PROF_SELF_ATTN = 0, MMPL_PROF_CROSS_ATTN = 1, MMPL_PROF_GEMM = 2, MMPL_PROF_POINTWISE = 3, MMPL_PROF_NCAT = 4 };
 int mmpl_profile_enable(mmpl_ctx* ctx, int category_mask);
+int mmpl_profile_mask(mmpl_ctx* ctx); /* the mask currently set */
 int mmpl_profile_read(mmpl_ctx* ctx, double* ms, double* work, int64_t* launches, int reset);
 /* The same spans split by call site inside CausalWanAttentionBlock.forward (causal_model.py:274-326): arrays of
  * MMPL_SITE_COUNT entries. Diagnostic only (bench.py "breakdown.sites", tools/). */

@@ -13,7 +13,7 @@ from pathlib import Path
 from . import _build
 
 _LIB = None
-ABI_VERSION = 3  # == MMPL_ABI_VERSION in include/mmpl_b200.h (tests/test_abi.py checks the header)
+ABI_VERSION = 4  # == MMPL_ABI_VERSION in include/mmpl_b200.h (tests/test_abi.py checks the header)
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
 c_int_p = C.POINTER(C.c_int)
@@ -96,6 +96,9 @@ SIGNATURES = {
     "mmpl_forward": (c_int, [c_void_p, C.POINTER(ForwardArgs), c_void_p]),
     "mmpl_total_launches": (c_int64, [c_int]),
     "mmpl_profile_enable": (c_int, [c_void_p, c_int]),
+    "mmpl_profile_mask": (c_int, [c_void_p]),
+    "mmpl_launch_credit": (c_int64, [c_void_p, c_int64]),
+    "mmpl_workspace_generation": (c_int64, []),
     "mmpl_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),
     "mmpl_profile_read_sites": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),
 }

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -127,6 +128,8 @@ class CausalWanModel(nn.Module):
         self._rope_table = None
         self._index_mirror: Dict[int, dict] = {}
         self._param_list = None
+        self._graphs: Dict[tuple, object] = {}
+        self._graph_generation = -1
         self.last_x0 = None
 
     # ------------------------------------------------------------------------------------------- init
@@ -171,6 +174,7 @@ class CausalWanModel(nn.Module):
         self._param_list = None
         self._bound_sig = None
         self._index_mirror.clear()
+        self._graphs.clear()
 
     def _apply(self, fn, *args, **kwargs):
         self._param_list = None  # parameters may be replaced by .to() / .cuda()
@@ -190,6 +194,7 @@ class CausalWanModel(nn.Module):
         if self._ctx is not None and tokens > self._ctx_tokens:
             lib.mmpl_ctx_destroy(self._ctx)
             self._ctx, self._bound_sig, self._rope_table = None, None, None
+            self._graphs.clear()
         if self._ctx is None:
             cap = max(tokens, 3 * 1560)
             cfg = _lib.ModelConfig(self.dim, self.ffn_dim, self.num_heads, self.num_layers, self.freq_dim, self.text_dim,
@@ -207,6 +212,7 @@ class CausalWanModel(nn.Module):
             _lib.check(lib.mmpl_bind_rope_table(self._ctx, self._rope_table.data_ptr()))
 
     def _bind_weights(self, lib):
+        self._graphs.clear()   # captured launch sequences hold the old weight pointers
         self._fused = []
         sd = dict(self.named_parameters())
 
@@ -334,6 +340,29 @@ class CausalWanModel(nn.Module):
         flow = torch.empty((B, Fn, self.out_dim, Hh, Ww), dtype=torch.bfloat16, device=dev)
 
         plan = self._make_plan(kv_cache, current_start, Fn, fs)
+        for d in kv_cache:
+            if d["k"].dtype != torch.bfloat16 or not d["k"].is_contiguous() or not d["v"].is_contiguous():
+                raise RuntimeError("kv_cache tensors must be contiguous bfloat16 [B, rows, heads, 128]")
+        ptrs = tuple(t.data_ptr() for d in kv_cache for t in (d["k"], d["v"])) + \
+            tuple(t.data_ptr() for c in crossattn_cache for t in (c["k"], c["v"]))
+        io = dict(x=x, t64=t64, sigma=sigma, flow=flow, x0=x0 if sigma is not None else None)
+        if self._graph_ok(S, B, need_cross):
+            key = (B, Cc, Fn, Hh, Ww, tuple(plan.frame_pos), tuple(plan.kv_row), tuple(plan.segments), bool(plan.kv_to_tail),
+                   sigma is not None, ptrs)
+            io = self._run_graphed(key, io, plan, kv_cache, crossattn_cache, dev)
+        else:
+            self._launch(io, context, plan, kv_cache, crossattn_cache, need_cross, dev)
+        if need_cross:
+            for c in crossattn_cache:
+                c["is_init"] = True  # model.py:175
+        self.last_x0 = io["x0"]
+        return io["flow"].permute(0, 2, 1, 3, 4)
+
+    def _launch(self, io, context, plan, kv_cache, crossattn_cache, need_cross, dev):
+        """One mmpl_forward per sample on the current stream of `dev`."""
+        lib = _lib.load()
+        x, t64, sigma, flow, x0 = io["x"], io["t64"], io["sigma"], io["flow"], io["x0"]
+        B, _, Fn, Hh, Ww = x.shape
         L = self.num_layers
         cache_rows = kv_cache[0]["k"].shape[1]
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -343,9 +372,6 @@ class CausalWanModel(nn.Module):
         frame_pos = (C.c_int * Fn)(*plan.frame_pos)
         kv_row = (C.c_int * Fn)(*plan.kv_row)
         for b in range(B):
-            for d in kv_cache:
-                if d["k"].dtype != torch.bfloat16 or not d["k"][b].is_contiguous() or not d["v"][b].is_contiguous():
-                    raise RuntimeError("kv_cache tensors must be contiguous bfloat16 [B, rows, heads, 128]")
             kv_k = (C.c_void_p * L)(*[d["k"][b].data_ptr() for d in kv_cache])
             kv_v = (C.c_void_p * L)(*[d["v"][b].data_ptr() for d in kv_cache])
             ck = (C.c_void_p * L)(*[c["k"][b].data_ptr() for c in crossattn_cache])
@@ -360,11 +386,57 @@ class CausalWanModel(nn.Module):
                 flow=flow[b].data_ptr(), x0=x0[b].data_ptr() if sigma is not None else None,
                 sigma=sigma[b].data_ptr() if sigma is not None else None)
             _lib.check(lib.mmpl_forward(self._ctx, C.byref(args), stream))
-        if need_cross:
-            for c in crossattn_cache:
-                c["is_init"] = True  # model.py:175
-        self.last_x0 = x0 if sigma is not None else None
-        return flow.permute(0, 2, 1, 3, 4)
+
+    # --------------------------------------------------------------------------------------------- CUDA graphs
+    # A forward is ~13 launches per block. At the benchmark's sizes (S = 4680, >= 16 ms of kernels per forward) the host
+    # stays far ahead of the GPU; at small ones (BASELINE config 0: S = 1170, ~3 ms of kernels behind ~400 launches) the
+    # launches themselves are the time. There the whole launch sequence of a forward is captured once per call shape -
+    # (latent shape, RoPE positions, cache rows written and attended, cache tensors) - into a CUDA graph over static
+    # input / output buffers and replayed: same kernels, same order, same arguments, one launch from the host.
+    graph_max_tokens = 2048     # forwards with more new tokens than this are not launch-bound: no capture
+    _graph_cap = 64
+
+    def _graph_ok(self, S: int, B: int, need_cross: bool) -> bool:
+        if S > self.graph_max_tokens or need_cross or os.environ.get("MMPL_CUDA_GRAPHS", "1") == "0":
+            return False
+        if torch.cuda.is_current_stream_capturing():
+            return False       # the caller is capturing a graph of its own: just launch into it
+        return _lib.load().mmpl_profile_mask(self._ctx) == 0    # per-launch timing events cannot live inside a graph
+
+    def _run_graphed(self, key, io, plan, kv_cache, crossattn_cache, dev):
+        lib = _lib.load()
+        generation = lib.mmpl_workspace_generation()
+        if generation != self._graph_generation:   # a workspace of the library moved: every captured pointer to it is stale
+            self._graphs.clear()
+            self._graph_generation = generation
+        entry = self._graphs.get(key)
+        if entry is None:
+            # first sighting: run eagerly (lazy initialisation inside the library - workspaces, tensor maps, function
+            # attributes - must not happen during a capture), remember the shape
+            if len(self._graphs) >= self._graph_cap:
+                self._graphs.clear()
+            self._graphs[key] = False
+            self._launch(io, None, plan, kv_cache, crossattn_cache, False, dev)
+            return io
+        if entry is False:
+            static = {k: (None if v is None else torch.empty_like(v, memory_format=torch.contiguous_format)) for k, v in io.items()}
+            for k in ("x", "t64", "sigma"):
+                if io[k] is not None:
+                    static[k].copy_(io[k])
+            graph = torch.cuda.CUDAGraph()
+            before = lib.mmpl_launch_count(self._ctx, 0)
+            with torch.cuda.graph(graph):
+                self._launch(static, None, plan, kv_cache, crossattn_cache, False, dev)
+            entry = self._graphs[key] = dict(graph=graph, static=static, launches=lib.mmpl_launch_count(self._ctx, 0) - before)
+            lib.mmpl_launch_credit(self._ctx, -entry["launches"])   # counted at capture, executed only by the replay below
+        static = entry["static"]
+        for k in ("x", "t64", "sigma"):
+            if io[k] is not None:
+                static[k].copy_(io[k])
+        entry["graph"].replay()
+        lib.mmpl_launch_credit(self._ctx, entry["launches"])
+        # the static outputs are overwritten by the next replay of this shape: hand out copies
+        return dict(io, flow=static["flow"].clone(), x0=None if static["x0"] is None else static["x0"].clone())
 
     def _make_plan(self, kv_cache, current_start, num_frames, frame_seqlen) -> AttendPlan:
         if isinstance(current_start, (list, tuple)) or (torch.is_tensor(current_start) and current_start.dim() > 0):

@@ -385,6 +385,17 @@ static cudaEvent_t prof_event(mmpl_ctx* ctx) {
     ++g_total_launches;                                                       \
   } while (0)
 
+int64_t mmpl_workspace_generation(void) { return workspace_generation(); }
+
+int mmpl_profile_mask(mmpl_ctx* ctx) { return ctx ? ctx->profile_mask : 0; }
+
+int64_t mmpl_launch_credit(mmpl_ctx* ctx, int64_t n) {
+  if (!ctx) return 0;
+  ctx->launches += n;
+  g_total_launches += n;
+  return ctx->launches;
+}
+
 int mmpl_profile_enable(mmpl_ctx* ctx, int category_mask) {
   MMPL_CHECK(ctx, MMPL_ERR_ARG, "profile_enable: null context");
   ctx->profile_mask = category_mask;

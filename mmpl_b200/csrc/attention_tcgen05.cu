@@ -1116,6 +1116,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
       g_part_bytes = 0;
       MMPL_CUDA(cudaMalloc(&g_part, need));
       g_part_bytes = need;
+      bump_workspace_generation();
     }
     p.part_o = g_part;
     p.part_ml = g_part + slots * kUnitRows * kHD;
@@ -1135,6 +1136,7 @@ int flash_attn_impl(const void* q, int64_t ldq, int Lq, int H, const void* k0, c
         MMPL_CUDA(cudaMalloc(&g_merge_cnt, need_cnt * sizeof(int)));
         MMPL_CUDA(cudaMemset(g_merge_cnt, 0, need_cnt * sizeof(int)));
         g_merge_cnt_n = need_cnt;
+        bump_workspace_generation();
       }
       p.merge_cnt = g_merge_cnt;
     }

@@ -663,6 +663,7 @@ static int ensure_streamk_workspace(int pairs) {
   g_sk_pairs = 0;
   MMPL_CUDA(cudaMalloc(&g_sk_part, static_cast<size_t>(pairs) * 2 * 128 * kPairBN * sizeof(float)));
   MMPL_CUDA(cudaMalloc(&g_sk_flags, static_cast<size_t>(pairs) * 2 * sizeof(uint32_t)));
+  bump_workspace_generation();
   MMPL_CUDA(cudaMemset(g_sk_flags, 0, static_cast<size_t>(pairs) * 2 * sizeof(uint32_t)));
   g_sk_pairs = pairs;
   return MMPL_OK;

@@ -110,6 +110,10 @@ void clear_tensor_map_cache() {
   g_maps.clear();
 }
 
+static int64_t g_workspace_generation = 0;
+int64_t workspace_generation() { return g_workspace_generation; }
+void bump_workspace_generation() { ++g_workspace_generation; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

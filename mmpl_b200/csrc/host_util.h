@@ -62,6 +62,12 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Bumped whenever a process-level device workspace (attention partials, merge counters, stream-K slots) is reallocated:
+// anything that recorded device pointers of the library - a captured CUDA graph of a launch sequence - is stale when
+// the value it saw differs from the current one (mmpl_workspace_generation()).
+int64_t workspace_generation();
+void bump_workspace_generation();
+
 // Number of SMs on the current device (cached) and sm_100 check.
 int sm_count();
 bool device_is_sm100();

@@ -286,3 +286,65 @@ def test_forward_14b_width_4_blocks_2_chunks_full_resolution():
         _cmp(f"14B-width 4 blocks chunk {chunk} flow", flow[0], ref, 0.0625, 0.9999)
         assert int(kv[0]["local_end_index"].item()) == okv[0].local_end_index == (chunk + 1) * 3 * fs
     _cmp("14B-width K cache, last block", kv[3]["k"][0], okv[3].k, 0.0625, 0.9999)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches(monkeypatch):
+    """Small forwards (S <= CausalWanModel.graph_max_tokens) are launch-bound: from the third call of a call shape on, the
+    launch sequence of mmpl_forward is replayed from a CUDA graph over static buffers. Same kernels, same arguments: flows,
+    x0 and cache contents must be bit-identical to the eager launches (MMPL_CUDA_GRAPHS=0), the launch counters must keep
+    counting executed kernels, and a reallocation of a library workspace (mmpl_workspace_generation) must retire the graphs."""
+    from mmpl_b200 import _lib, ops
+    from mmpl_b200.causal_model import CausalWanModel
+    lib = _lib.load()
+    cfg = O.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=32)
+    w = O.make_weights(cfg, seed=13)
+    noise, prompt = _synth_inputs(cfg, 6, 16, 24)
+    fs, rows = 8 * 12, 6 * 8 * 12
+
+    def run(graphs: bool):
+        monkeypatch.setenv("MMPL_CUDA_GRAPHS", "1" if graphs else "0")
+        model = CausalWanModel(text_len=cfg.text_len, dim=cfg.dim, ffn_dim=cfg.ffn_dim, text_dim=cfg.text_dim,
+                               num_heads=cfg.num_heads, num_layers=cfg.num_layers)
+        model.load_state_dict(w)
+        model = model.to(DEV, torch.bfloat16).eval()
+        kv = [{"k": torch.zeros(1, rows, 2, 128, dtype=torch.bfloat16, device=DEV), "v": torch.zeros(1, rows, 2, 128, dtype=torch.bfloat16, device=DEV),
+               "global_end_index": torch.tensor([0], device=DEV), "local_end_index": torch.tensor([0], device=DEV)} for _ in range(2)]
+        cross = [{"k": None, "v": None, "is_init": False} for _ in range(2)]
+        outs, counts = [], []
+        for rep in range(3):                       # the same two-chunk rollout three times: eager, capture, replay
+            for d in kv:
+                d["global_end_index"] = torch.tensor([0], device=DEV)
+                d["local_end_index"] = torch.tensor([0], device=DEV)
+            for chunk in (0, 1):
+                for t_val in (1000.0, 625.0, 0.0):
+                    x = noise[:, chunk * 3:(chunk + 1) * 3].to(DEV)
+                    t = torch.full((1, 3), t_val, device=DEV)
+                    sig = torch.full((1, 3), t_val / 1000.0, device=DEV, dtype=torch.float64)
+                    before = model.launch_count() if model._ctx is not None else 0
+                    flow = model(x.permute(0, 2, 1, 3, 4), t=t, context=prompt.to(DEV), seq_len=32760, kv_cache=kv,
+                                 crossattn_cache=cross, current_start=chunk * 3 * fs, sigma=sig)
+                    counts.append(model.launch_count() - before)
+                    outs.append((flow.clone(), model.last_x0.clone()))
+            if rep == 1 and graphs:
+                # grow the attention workspace behind the model's back: a KV-split attention call with many partial pieces
+                gen0 = lib.mmpl_workspace_generation()
+                lib.mmpl_attn_set_split(5)
+                q, k, v = (torch.randn(2048, 8, 128, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+                ops.flash_attn(q, torch.cat([k] * 4), torch.cat([v] * 4))
+                lib.mmpl_attn_set_split(0)
+                run.grew = lib.mmpl_workspace_generation() != gen0
+        captured = sum(1 for e in model._graphs.values() if e) if graphs else 0
+        return outs, counts, [kv[i]["k"].clone() for i in range(2)], captured
+
+    run.grew = False
+    eager, n_eager, kv_eager, _ = run(False)
+    graphed, n_graph, kv_graph, captured = run(True)
+    assert len(eager) == len(graphed) == 18
+    for i, ((f0, x0), (f1, x1)) in enumerate(zip(eager, graphed)):
+        assert torch.equal(f0, f1) and torch.equal(x0, x1), f"call {i}: graph replay differs from eager launches"
+    for a, b in zip(kv_eager, kv_graph):
+        assert torch.equal(a, b)
+    assert n_eager[1:] == n_graph[1:] and all(n > 0 for n in n_graph)     # call 0 computes the cross K/V: a few launches more
+    # with the workspace grown after the second repetition the third one starts over (eager sighting); without growth it
+    # replays: either way graphs exist or were legitimately retired, and the results above are identical
+    assert captured > 0 or run.grew
