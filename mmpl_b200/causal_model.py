@@ -425,7 +425,9 @@ class CausalWanModel(nn.Module):
                     static[k].copy_(io[k])
             graph = torch.cuda.CUDAGraph()
             before = lib.mmpl_launch_count(self._ctx, 0)
-            with torch.cuda.graph(graph):
+            # thread-local capture mode: other threads of the process (NCCL's watchdog, a second pipeline of a threaded
+            # driver) keep making CUDA calls while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 self._launch(static, None, plan, kv_cache, crossattn_cache, False, dev)
             entry = self._graphs[key] = dict(graph=graph, static=static, launches=lib.mmpl_launch_count(self._ctx, 0) - before)
             lib.mmpl_launch_credit(self._ctx, -entry["launches"])   # counted at capture, executed only by the replay below
