@@ -516,12 +516,24 @@ def run_ours(args):
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        chain = run_chain(args, rank, world, device, deadline=t_start + args.time_budget)
+        # a failure in the chain measurement must not cost the cfg2 line: it is recorded in the line instead
+        try:
+            chain = run_chain(args, rank, world, device, deadline=t_start + args.time_budget)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            chain, chain_failed = {"error": f"{type(e).__name__}: {e}"}, True
+        else:
+            chain_failed = False
         if rank == 0:
             out["chain"] = chain
+    else:
+        chain_failed = False
     if rank == 0:
         out["wall_s"] = round(time.perf_counter() - t_start, 1)
         emit(out)
+    if chain_failed:
+        os._exit(0)   # peers may be stuck in a collective of the failed measurement: leave without the group's shutdown handshake
     if world > 1:
         dist.destroy_process_group()
 
