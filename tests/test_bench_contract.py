@@ -49,3 +49,14 @@ def test_reference_arm_prints_one_contract_line():
     assert d["config"]["same_config"] is True and d["steps"] == 2 and d["warmup"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_chain_layouts_per_world_size():
+    """The layouts bench.py's `chain` record measures at each N (tools/chain_bench.py), as run on 1 / 2 / 4 / 8 B200."""
+    from tools.chain_bench import chain_layouts
+    L = lambda n: [(v["chains"], v["slots"], v["lanes"]) for v in chain_layouts(n)]
+    assert L(1) == [(1, 1, 1)]
+    assert L(2) == [(1, 1, 2)]
+    assert L(4) == [(2, 1, 2), (1, 2, 2)]
+    assert L(8) == [(2, 2, 2), (1, 4, 2), (4, 1, 2)]
+    assert all(c * s * l == n for n in (1, 2, 4, 8) for c, s, l in L(n))

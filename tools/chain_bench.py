@@ -51,6 +51,20 @@ def segment_flops(dims: dict, steps: int, i2v: bool = False, first: bool = True)
     return total
 
 
+def chain_layouts(world: int) -> List[dict]:
+    """Every layout chains x slots x lanes = world worth measuring, most informative first: lanes = 2 (CFG pair) from two
+    ranks up; chain counts are the powers of two that leave every chain at least one whole slot; two chains first on a box
+    that has them (the layout that fills 8 GPUs), then the single long video, then the narrower ones."""
+    lanes = 2 if world >= 2 else 1
+    slots_total = world // lanes
+    out, chains = [], 1
+    while chains <= slots_total and slots_total % chains == 0 and world % chains == 0:
+        out.append(dict(chains=chains, slots=slots_total // chains, lanes=lanes))
+        chains *= 2
+    order = {2: 0, 1: 1}
+    return sorted(out, key=lambda v: order.get(v["chains"], v["chains"]))
+
+
 class ChainBench:
     """Everything that is built once per process: the 14B replica, the pipeline (with its CFG-pair group), the VAE and every
     rank group the variants need."""
@@ -118,15 +132,7 @@ class ChainBench:
 
     def variants(self) -> List[dict]:
         """Layouts worth measuring on this world size, most informative first."""
-        slots_total = self.world // self.lanes
-        out = []
-        chains = 1
-        while chains in self.chain_groups and slots_total % chains == 0:
-            out.append(dict(chains=chains, slots=slots_total // chains, lanes=self.lanes))
-            chains *= 2
-        # two chains first on a full box (the layout that fills 8 GPUs), then the single long video, then the rest
-        order = {2: 0, 1: 1}
-        return sorted(out, key=lambda v: order.get(v["chains"], v["chains"]))
+        return [v for v in chain_layouts(self.world) if v["chains"] in self.chain_groups]
 
     # -------------------------------------------------------------------------------------------------------------- run
     def run(self, chains: int, segments_per_chain: int, sampling_steps: Optional[int] = None, warm: bool = False) -> Optional[dict]:
