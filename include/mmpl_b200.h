@@ -54,7 +54,9 @@ const char* mmpl_last_error(void);
 
 /* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]); replaces nn.Linear (+ fused follow-up op).
  * lda/ldw/ldo/ldr are row pitches in elements. residual may alias out. gate is [frames][gate_stride]
- * (row r uses frame r / rows_per_frame). tile_n: 0 = auto, or 64/128/256. */
+ * (row r uses frame r / rows_per_frame). tile_n: 0 = auto; 64/128/192/256 = single-CTA tiles of that width; 512/448 =
+ * cta_group::2 pairs (256 x 256 / 256 x 224 per pair); 1128/1192 = clusters of two 128 x 128 / 128 x 192 tiles that
+ * share their A tile by TMA multicast (needs an even number of tiles along N). */
 int mmpl_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* out,
                    int64_t ldo, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
                    const void* gate, int64_t gate_stride, int rows_per_frame, int tile_n, void* stream);

@@ -63,7 +63,7 @@ struct ParamsOf<true> { using type = ConvGemmParams; };
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -362,6 +362,170 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared-A variant of the kernel above for the short-K projections (cfg2's o / cross-q / cross-o, M = 4680, N = K = 1536).
+// Their 128 x 128 tiles fit the machine exactly (444 = 3 x 148) but load 32 KB per 64-wide k block for 256 clk of MMA,
+// 128 B/clk/SM, above what L2 delivers to one SM (measured 341 clk per k block); the cta_group::2 tiles halve the bytes
+// but quantise M into 4 waves. Here a cluster of two CTAs computes two 128 x BN tiles that are neighbours along N, i.e.
+// share their A rows: each CTA loads its own W tile and HALF of the A tile (64 rows), which TMA multicasts into the
+// shared memory of both. 8 + 16 KB per CTA and k block at BN = 128 (96 B/clk/SM, 222 cluster tiles = 3 waves on 74
+// clusters), 8 + 24 KB at BN = 192 (85 B/clk/SM, 148 cluster tiles = 2 waves). Each CTA runs its own cta_group::1 MMAs
+// on its own TMEM; only the shared-memory ring is coupled:
+//   full[s]  (per CTA, 1 arrival + bytes): the CTA's own producer arms it with the bytes that land in ITS shared memory
+//            (both A halves + its W tile); the peer's multicast credits its half to the barrier at the same offset here.
+//   empty[s] (per CTA, 2 arrivals): a slot is rewritten by both producers, so it is free only once the MMAs of BOTH CTAs
+//            have read it: each MMA warp commits to empty[s] of both CTAs (multicast commit).
+// A peer's bytes may be credited before the local producer has armed the phase: the phase cannot complete without the
+// producer's own arrival, and they cannot arrive a phase early because the peer's producer waits for this CTA's MMA
+// commit of the previous use of the slot, which follows this CTA's full[s] wait.
+__device__ __forceinline__ void tma_load_2d_mcast_elect(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                                        int32_t c1, uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1),
+      "l"(policy)
+      : "memory");
+}
+// Commit of this CTA's tcgen05 ops, arriving on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void tc_commit_mcast_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_shared_a_kernel(const __grid_constant__ CUtensorMap map_a /* box: 64 rows */, const __grid_constant__ CUtensorMap map_b,
+                          const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int ST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + ST * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + ST;
+  uint64_t* tmem_full = bars + 2 * ST;
+  uint64_t* tmem_empty = bars + 2 * ST + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta = static_cast<int>(cluster_ctarank());
+  const int cluster = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int num_tiles = p.tiles_m * (p.tiles_n >> 1);  // cluster tiles of 128 x 2 BN; tiles_n is even (host)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < ST; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 2);  // the MMA warps of both CTAs
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], kEpiWarps);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  cluster_sync();  // the peer's barriers are initialised before anything of this CTA can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL (see gemm_bf16_kernel)
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = cluster; t < num_tiles; t += num_clusters) {
+      const int m_blk = t % p.tiles_m;
+      const int n_blk = 2 * (t / p.tiles_m) + cta;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx_elect(&full_bar[s], Cfg::kStageBytes);
+        // rows [64 cta, 64 cta + 64) of the A tile, into both CTAs at the same offset
+        tma_load_2d_mcast_elect(smem_a + s * Cfg::kABytes + cta * (Cfg::kABytes / 2), &map_a, &full_bar[s], kb * kBK,
+                                m_blk * kBM + cta * (kBM / 2), 0x3, kEvictNormal);
+        tma_load_2d_elect(smem_b + s * Cfg::kBBytes, &map_b, &full_bar[s], kb * kBK, n_blk * BN, kEvictLast);
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = cluster; t < num_tiles; t += num_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        constexpr uint64_t kDesc0 = make_smem_desc_sw128_const(16, 1024);
+        const uint32_t a_lo = desc_lo(kDesc0) + ((smem_u32(smem_a) + s * Cfg::kABytes) >> 4);
+        const uint32_t b_lo = desc_lo(kDesc0) + ((smem_u32(smem_b) + s * Cfg::kBBytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          umma_ss_elect(tmem_d, a_lo + 2 * k, desc_hi(kDesc0), b_lo + 2 * k, desc_hi(kDesc0), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit_mcast_elect(&empty_bar[s], 0x3);
+        if (kb == num_kb - 1) tc_commit_elect(&tmem_full[as]);
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int lane_base = (warp & 3) * 32;
+    int it = 0;
+    for (int t = cluster; t < num_tiles; t += num_clusters, ++it) {
+      const int m_blk = t % p.tiles_m;
+      const int n_blk = 2 * (t / p.tiles_m) + cta;
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      const int row = m_blk * kBM + lane_base + lane;
+      const int half = (warp - 2) >> 2;
+      constexpr int kChunks = BN / 32 / 2;
+      static_assert((BN / 32) % 2 == 0, "shared-A tile width");
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(lane_base) << 16) + as * BN, row, n_blk * BN,
+                             half * kChunks, (half + 1) * kChunks);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();  // no CTA leaves while the peer's multicast loads or commits can still reach its shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -771,6 +935,43 @@ static int dispatch_epi(int epi, const CUtensorMap* ma, const CUtensorMap* mb, c
   }
 }
 
+// Shared-A clusters (gemm_bf16_shared_a_kernel): two 128 x BN tiles per cluster, N must hold an even number of tiles.
+template <int BN, int EPI>
+static int launch_gemm_shared_a(const CUtensorMap* ma, const CUtensorMap* mb, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_shared_a_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + kBM - 1) / kBM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const int tiles = p.tiles_m * (p.tiles_n / 2);
+  const int max_clusters = sm_count() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  MMPL_CUDA_LAUNCH(launch_kernel(kern, 2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream, *ma, *mb, p));
+  MMPL_CUDA(cudaGetLastError());
+  return MMPL_OK;
+}
+
+template <int BN>
+static int dispatch_epi_shared_a(int epi, const CUtensorMap* ma, const CUtensorMap* mb, const GemmParams& p,
+                                 cudaStream_t stream) {
+  switch (epi) {
+    case MMPL_EPI_BIAS: return launch_gemm_shared_a<BN, MMPL_EPI_BIAS>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GELU: return launch_gemm_shared_a<BN, MMPL_EPI_BIAS_GELU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_SILU: return launch_gemm_shared_a<BN, MMPL_EPI_BIAS_SILU>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_RES: return launch_gemm_shared_a<BN, MMPL_EPI_BIAS_RES>(ma, mb, p, stream);
+    case MMPL_EPI_BIAS_GATE_RES: return launch_gemm_shared_a<BN, MMPL_EPI_BIAS_GATE_RES>(ma, mb, p, stream);
+    default: set_error("gemm: unknown epilogue %d", epi); return MMPL_ERR_ARG;
+  }
+}
+
+// Kernel for the short-K shapes that gemm_bf16() takes off the pair kernel (see there): 128 until the B200 A/B of the
+// candidates says otherwise.
+constexpr int kShortKDefault = 128;
+
 // Tile width: 256 when it keeps the machine full, otherwise narrower tiles for more CTAs.
 static int pick_bn(int M, int N) {
   if (N % 128 != 0 || N < 128) return 64;
@@ -812,8 +1013,33 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     const double fill_single = double(ts) / (double((ts + sms - 1) / sms) * sms);
     if (fill_pair < 0.8 && fill_single > 0.95) {
       use_pair = false;
+      // which short-K kernel: 128 = single-CTA 128 x 128 tiles; 192 = single-CTA 128 x 192; 1128 / 1192 = shared-A
+      // clusters of two 128 x 128 / 128 x 192 tiles (gemm_bf16_shared_a_kernel). MMPL_GEMM_SHORT_K overrides (A/B).
+      static const int env_sk = getenv("MMPL_GEMM_SHORT_K") ? atoi(getenv("MMPL_GEMM_SHORT_K")) : 0;
+      const int want = env_sk ? env_sk : kShortKDefault;
       force_bn = 128;
+      if (want == 192 && N % 192 == 0) force_bn = 192;
+      if (want == 1128) force_bn = 1128;  // N % 256 == 0 here: an even number of 128-wide tiles
+      if (want == 1192 && N % 384 == 0) force_bn = 1192;
     }
+  }
+  if (force_bn == 1128 || force_bn == 1192) {
+    const int bn = force_bn - 1000;
+    MMPL_CHECK(((N + bn - 1) / bn) % 2 == 0, MMPL_ERR_ARG, "gemm: shared-A clusters need an even number of %d-wide tiles (N=%d)", bn, N);
+    const CUtensorMap* ma = get_tensor_map_bf16(a, M, K, lda, kBM / 2);  // each CTA loads (and multicasts) half of the A tile
+    const CUtensorMap* mb = get_tensor_map_bf16(w, N, K, ldw, bn);
+    if (!ma || !mb) return MMPL_ERR_CUDA;
+    GemmParams pp{};
+    pp.M = M; pp.N = N; pp.K = K;
+    pp.out = static_cast<__nv_bfloat16*>(out);
+    pp.ldo = ldo;
+    pp.bias = static_cast<const __nv_bfloat16*>(bias);
+    pp.res = static_cast<const __nv_bfloat16*>(residual);
+    pp.ldr = ldr;
+    pp.gate = static_cast<const __nv_bfloat16*>(gate);
+    pp.gate_stride = gate_stride;
+    pp.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
+    return bn == 192 ? dispatch_epi_shared_a<192>(epilogue, ma, mb, pp, stream) : dispatch_epi_shared_a<128>(epilogue, ma, mb, pp, stream);
   }
   if (use_pair) {
     MMPL_CHECK(N % 8 == 0, MMPL_ERR_SHAPE, "gemm: N must be a multiple of 8");
@@ -835,7 +1061,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     return pbn == 224 ? dispatch_epi_pair<224>(epilogue, pa, pb, pp, stream) : dispatch_epi_pair<256>(epilogue, pa, pb, pp, stream);
   }
   const int bn = force_bn ? force_bn : pick_bn(M, N);
-  MMPL_CHECK(bn == 64 || bn == 128 || bn == 256, MMPL_ERR_ARG, "gemm: tile width %d not supported", bn);
+  MMPL_CHECK(bn == 64 || bn == 128 || bn == 192 || bn == 256, MMPL_ERR_ARG, "gemm: tile width %d not supported", bn);
 
   const CUtensorMap* ma = get_tensor_map_bf16(a, M, K, lda, kBM);
   const CUtensorMap* mb = get_tensor_map_bf16(w, N, K, ldw, bn);
@@ -852,6 +1078,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   p.gate_stride = gate_stride;
   p.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
   if (bn == 256) return dispatch_epi<256>(epilogue, ma, mb, p, stream);
+  if (bn == 192) return dispatch_epi<192>(epilogue, ma, mb, p, stream);
   if (bn == 128) return dispatch_epi<128>(epilogue, ma, mb, p, stream);
   return dispatch_epi<64>(epilogue, ma, mb, p, stream);
 }

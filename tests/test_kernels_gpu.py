@@ -48,6 +48,12 @@ def _report(name, got, ref, atol, rtol, outlier_frac=0.0, outlier_abs=0.0):
     # tile 448 = the cta_group::2 kernel with 256 x 224 tiles (N tail: 1536 = 6 x 224 + 192, 512 = 2 x 224 + 64)
     (256, 224, 64, 448), (300, 512, 192, 448), (4680, 1536, 1536, 448), (4680, 1536, 8960, 448), (4680, 4608, 1536, 448),
     (1170, 1536, 1536, 448), (10920, 5120, 5120, 448),
+    # tile 192 = single-CTA 128 x 192 tiles (N tail: 512 = 2 x 192 + 128)
+    (128, 192, 64, 192), (300, 512, 192, 192), (4680, 1536, 1536, 192), (1170, 1536, 1536, 192),
+    # tiles 1128 / 1192 = clusters of two 128 x 128 / 128 x 192 tiles sharing the A tile by TMA multicast (M tails of 44 and
+    # 72 rows: the second half of the A tile partly or wholly out of bounds; N tail: 640 = 3 x 192 + 64)
+    (128, 256, 64, 1128), (300, 512, 192, 1128), (4680, 1536, 1536, 1128), (1170, 1536, 1536, 1128), (10920, 5120, 5120, 1128),
+    (128, 384, 64, 1192), (300, 640, 192, 1192), (4680, 1536, 1536, 1192), (1170, 1536, 1536, 1192), (300, 768, 1024, 1192),
 ])
 def test_gemm_bias(M, N, K, tile):
     ops = _ops()
@@ -57,7 +63,8 @@ def test_gemm_bias(M, N, K, tile):
 
 
 @pytest.mark.parametrize("M,N,K,tile", [(1170, 1536, 1536, 0), (4680, 1536, 1536, 0), (4680, 1536, 1536, 128), (1170, 1536, 1536, 512),
-                                        (4680, 1536, 1536, 448), (4680, 1536, 8960, 0), (1170, 1536, 1536, 448)])
+                                        (4680, 1536, 1536, 448), (4680, 1536, 8960, 0), (1170, 1536, 1536, 448),
+                                        (4680, 1536, 1536, 192), (4680, 1536, 1536, 1128), (4680, 1536, 1536, 1192)])
 def test_gemm_epilogues(M, N, K, tile):
     import functools
     ops = _ops()

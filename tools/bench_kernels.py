@@ -124,8 +124,11 @@ if __name__ == "__main__":
     ap.add_argument("--what", default="gemm,attn")
     a = ap.parse_args()
     if "gemm" in a.what:
-        bench_gemm([(4680, 4608, 1536), (4680, 1536, 1536), (4680, 8960, 1536), (4680, 1536, 8960),
-                    (10920, 15360, 5120), (10920, 5120, 5120), (10920, 13824, 5120), (10920, 5120, 13824)],
+        gemm_shapes = [(4680, 4608, 1536), (4680, 1536, 1536), (4680, 8960, 1536), (4680, 1536, 8960),
+                       (10920, 15360, 5120), (10920, 5120, 5120), (10920, 13824, 5120), (10920, 5120, 13824)]
+        if os.environ.get("GEMM_SHAPES"):  # e.g. "4680x1536x1536"
+            gemm_shapes = [tuple(int(v) for v in sh.split("x")) for sh in os.environ["GEMM_SHAPES"].split(",")]
+        bench_gemm(gemm_shapes,
                    tiles=[int(t) for t in os.environ.get('GEMM_TILES', '128,256,512').split(',')])
     if "attn" in a.what:
         shapes = [(4680, 4680, 12), (4680, 18720, 12), (4680, 32760, 12), (4680, 512, 12), (10920, 14040, 40)]
